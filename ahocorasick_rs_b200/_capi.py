@@ -1,0 +1,79 @@
+"""ctypes binding of include/acb200.h (libacb200.so).  No torch types cross
+this boundary: callers pass raw device pointers (tensor.data_ptr()) and the
+raw cudaStream_t."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libacb200.so")
+
+ACB_OK = 0
+ACB_EINVAL, ACB_EBUILD, ACB_EUNSUPPORTED, ACB_ECUDA, ACB_ECAPACITY = -1, -2, -3, -4, -5
+
+
+class Workspace(C.Structure):
+    _fields_ = [
+        ("dev_raw", C.c_void_p), ("dev_raw_seq", C.c_void_p), ("dev_raw_unit", C.c_void_p),
+        ("raw_capacity", C.c_uint64),
+        ("dev_unit_counts", C.c_void_p), ("dev_unit_offsets", C.c_void_p), ("dev_scratch", C.c_void_p),
+        ("dev_total", C.c_void_p), ("dev_out", C.c_void_p), ("out_capacity", C.c_uint64),
+    ]
+
+
+class Tuning(C.Structure):
+    _fields_ = [("kernel", C.c_int), ("hot_rows", C.c_int), ("ctas_per_sm", C.c_int)]
+
+
+_lib = None
+
+
+def lib():
+    """The loaded library.  Fails loudly when it has not been built: there is no
+    CPU fallback behind the matcher classes."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). ahocorasick_rs_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        L.acb_last_error.restype = C.c_char_p
+        L.acb_version.restype = C.c_char_p
+        L.acb_launch_count.restype = C.c_uint64
+        L.acb_set_tuning.argtypes = [C.POINTER(Tuning)]
+        L.acb_timing_enable.argtypes = [C.c_int]
+        L.acb_timing_read.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+        L.acb_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.acb_free.argtypes = [C.c_void_p]
+        for name, res in [("acb_num_patterns", C.c_uint64), ("acb_num_states", C.c_uint64),
+                          ("acb_num_columns", C.c_uint32), ("acb_max_pattern_len", C.c_uint32),
+                          ("acb_min_pattern_len", C.c_uint32), ("acb_match_kind", C.c_int),
+                          ("acb_image_bytes", C.c_uint64)]:
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = [C.c_void_p]
+        L.acb_image_write.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.acb_scratch_words.restype = C.c_uint64
+        L.acb_scratch_words.argtypes = [C.c_uint64]
+        L.acb_chunk_count.restype = C.c_uint64
+        L.acb_chunk_count.argtypes = [C.c_uint64, C.c_uint32]
+        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                                     C.POINTER(Workspace), C.c_void_p]
+        L.acb_scan_chunked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
+                                       C.POINTER(Workspace), C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().acb_last_error().decode("utf-8", "replace")
+
+
+EXPORTS = [
+    "acb_last_error", "acb_version", "acb_build", "acb_free", "acb_num_patterns", "acb_num_states",
+    "acb_num_columns", "acb_max_pattern_len", "acb_min_pattern_len", "acb_match_kind", "acb_image_bytes",
+    "acb_image_write", "acb_scratch_words", "acb_scan_batch", "acb_chunk_count", "acb_scan_chunked",
+    "acb_launch_count", "acb_set_tuning", "acb_timing_enable", "acb_timing_read",
+]

@@ -1,0 +1,59 @@
+// automaton.h -- host-side automaton and the flat device image the kernels read.
+//
+// Stands in for what AhoCorasickBuilder::build returns at
+// /root/reference/src/lib.rs:186-215 and 401-406 (the crate's NFA/DFA), laid
+// out for HBM rather than for a CPU cache: see DESIGN.md "Data layout".
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace acb {
+
+constexpr uint32_t kDead = 0;  // absorbing; only reachable under leftmost kinds
+constexpr uint32_t kRoot = 1;  // unanchored start state
+constexpr uint32_t kMatchFlag = 0x80000000u;  // set on a transition entry whose target is a match state
+constexpr uint32_t kStateMask = 0x7fffffffu;
+
+enum ColMode : uint32_t {
+    kColRange = 0,  // column = min(byte - lo, ncols - 1) (unsigned): no table lookup per byte
+    kColClass = 1,  // column = colmap[byte]
+};
+
+// Header of the device image.  Copied by value into kernel parameters; the
+// offsets are byte offsets from the start of the image.
+struct ImageHeader {
+    uint32_t magic;
+    uint32_t version;
+    uint32_t match_kind;
+    uint32_t col_mode;
+    uint32_t n_states;      // including kDead and kRoot
+    uint32_t n_cols;        // row width, in entries
+    uint32_t col_lo;        // kColRange: first byte that has its own column
+    uint32_t n_patterns;
+    uint32_t max_pat_len;
+    uint32_t min_pat_len;
+    uint32_t n_hot_eligible; // states are BFS ordered; rows [0, n_hot_eligible) may be cached on chip
+    uint32_t reserved;
+    uint64_t off_colmap;     // u8[256]
+    uint64_t off_trans;      // u32[n_states * n_cols]: next state | kMatchFlag
+    uint64_t off_match_off;  // u32[n_states + 1]
+    uint64_t off_match_pid;  // u32[match_off[n_states]]: own patterns first (ascending id), then suffixes, longest first
+    uint64_t off_pat_len;    // u32[n_patterns] bytes
+    uint64_t off_pat_cplen;  // u32[n_patterns] code points (non-continuation bytes)
+    uint64_t total_bytes;
+};
+
+constexpr uint32_t kImageMagic = 0x30424341u;  // "ACB0"
+
+struct Automaton {
+    ImageHeader hdr{};
+    std::vector<uint8_t> image;  // header + tables, ready to copy to the device
+    int implementation = -1;
+};
+
+// Builds the automaton; throws std::runtime_error with a message on failure.
+Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_t n, int match_kind,
+                           int implementation);
+
+}  // namespace acb

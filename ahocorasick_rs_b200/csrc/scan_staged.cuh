@@ -1,0 +1,211 @@
+// scan_staged.cuh -- the hot kernel: one lane per scan unit, hot table rows in
+// shared memory, haystack bytes staged through shared memory with cp.async.
+//
+// Layout per CTA (dynamic shared memory):
+//   [ hot table : (H + 1) rows x n_cols u16 ]  rows 0..H-1 are the H shallowest
+//        states (ids are breadth-first, so "shallow" = "low id"); row H is the
+//        TRAP row.  An entry is the next state if that state is < H and is
+//        neither a match state nor the dead state, else H.  The trap row maps
+//        everything to H, so a lane that left the hot set stays at H and ONE
+//        compare per 16 bytes detects it; the 16 bytes are then redone by
+//        exact_scan from the saved state.
+//   [ column map : 256 B ]  (kColClass only)
+//   [ staging : per warp, 2 buffers x 32 lanes x 64 B ]  lane l's 64-byte
+//        chunk, 16-byte units XOR-swizzled with (l >> 1) & 3 so the per-lane
+//        LDS.128 reads are bank-conflict free.
+//
+// Each lane walks its own unit in 64-byte chunks of the ABSOLUTE address grid,
+// so every cp.async is 16-byte aligned and a warp-wide copy instruction
+// touches 8 x 64 contiguous bytes.  Chunk k+1 is in flight while chunk k is
+// scanned (the scan of a chunk takes longer than an HBM round trip).
+#pragma once
+#include "scan_core.cuh"
+
+namespace acb {
+
+constexpr int kChunk = 64;            // bytes per lane per stage
+constexpr int kStageBytes = 32 * kChunk;  // per warp per buffer
+
+struct FastTab {
+    const uint16_t *hot;
+    const uint8_t *cmap;
+    uint32_t n_cols, lo, maxc, trap;
+};
+
+template <int COLMODE>
+__device__ __forceinline__ uint32_t fstep(uint32_t s, uint32_t b, const FastTab &f) {
+    const uint32_t col = (COLMODE == kColRange) ? min(b - f.lo, f.maxc) : (uint32_t)f.cmap[b];
+    return f.hot[s * f.n_cols + col];
+}
+
+template <int COLMODE>
+__device__ __forceinline__ uint32_t fstep4(uint32_t s, uint32_t w, const FastTab &f) {
+    s = fstep<COLMODE>(s, w & 0xffu, f);
+    s = fstep<COLMODE>(s, (w >> 8) & 0xffu, f);
+    s = fstep<COLMODE>(s, (w >> 16) & 0xffu, f);
+    s = fstep<COLMODE>(s, w >> 24, f);
+    return s;
+}
+
+// continuation bytes (10xxxxxx) in a word
+__device__ __forceinline__ uint32_t cont_bytes(uint32_t w) { return __popc(w & ~(w << 1) & 0x80808080u); }
+
+// advance the code point counter to position `to` (no-op when already there or past it)
+__device__ __forceinline__ void cp_catch_up(UnitCtx &c, uint32_t to) {
+    uint32_t p = c.cp_pos, n = c.cp_count;
+    while (p < to) {
+        n += (ld_u8(c.base + p) & 0xC0u) != 0x80u;
+        p++;
+    }
+    c.cp_pos = p;
+    c.cp_count = n;
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int MODE, bool CP, int COLMODE>
+__global__ void __launch_bounds__(1024, 1)
+scan_staged_kernel(DevImage im, Units U, Sink out, uint32_t H, uint32_t hot_bytes, unsigned int *task_counter) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint16_t *hot = reinterpret_cast<uint16_t *>(smem);
+    uint8_t *cmap = smem + hot_bytes;                       // 256 B
+    uint8_t *stage_all = smem + hot_bytes + 256;            // 128-aligned by construction
+
+    // ---- prologue: derive the hot table from the dense table (L2 resident) ----
+    {
+        const uint32_t n = (H + 1) * im.n_cols;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+            const uint32_t s = i / im.n_cols;
+            uint32_t v = H;
+            if (s != kDead && s < H) {
+                const uint32_t e = __ldg(im.trans + i);
+                const uint32_t t = e & kStateMask;
+                if (!(e & kMatchFlag) && t != kDead && t < H) v = t;
+            }
+            hot[i] = (uint16_t)v;
+        }
+        for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
+    }
+    __syncthreads();
+
+    FastTab ft;
+    ft.hot = hot;
+    ft.cmap = cmap;
+    ft.n_cols = im.n_cols;
+    ft.lo = im.col_lo;
+    ft.maxc = im.n_cols - 1;
+    ft.trap = H;
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *stage = stage_all + (size_t)warp * 2 * kStageBytes;
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const uintptr_t gbase = reinterpret_cast<uintptr_t>(U.bytes) & ~uintptr_t(kChunk - 1);
+    const uint32_t my_swz = (lane >> 1) & 3;
+
+    for (;;) {
+        // ---- claim the next 32 units -------------------------------------------
+        unsigned int task = 0;
+        if (lane == 0) task = atomicAdd(task_counter, 1u);
+        task = __shfl_sync(0xffffffffu, task, 0);
+        if ((int64_t)task * 32 >= U.n_units) break;
+
+        UnitCtx c;
+        const bool valid = init_unit<CP>(c, U, (int64_t)task * 32 + lane);
+        uint32_t phase = 0, off16 = 0, nchunks = 0;
+        int64_t rel0 = 0;  // position (relative to c.base) of the first byte of chunk 0
+        uint32_t pos = 0, s = kRoot;
+        if (valid) {
+            const uintptr_t p0 = reinterpret_cast<uintptr_t>(c.base + c.at);
+            const uintptr_t pe = reinterpret_cast<uintptr_t>(c.base + c.end);
+            const uintptr_t a0 = p0 & ~uintptr_t(kChunk - 1);
+            phase = (uint32_t)(0 - reinterpret_cast<uintptr_t>(c.base)) & 15u;
+            off16 = (uint32_t)((a0 - gbase) >> 4);
+            nchunks = (pe > a0) ? (uint32_t)((pe - a0 + kChunk - 1) / kChunk) : 0;
+            rel0 = (int64_t)c.at - (int64_t)(p0 - a0);
+            // head: bytes before the first 16-byte boundary
+            exact_scan<MODE, CP>(c, im, out, true, c.at, phase, H);
+            pos = c.at;
+            s = c.state;
+            if (CP) cp_catch_up(c, pos);
+        }
+        uint32_t kmax = nchunks;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+
+        // who loads what: copy instruction i moves 16-byte unit (i*32+lane)&3 of lane (i*32+lane)>>2
+        uint32_t src_off16[4], src_nch[4], dst_off[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = i * 32 + lane, ch = idx >> 2, un = idx & 3;
+            src_off16[i] = __shfl_sync(0xffffffffu, off16, ch) + un;
+            src_nch[i] = __shfl_sync(0xffffffffu, nchunks, ch);
+            dst_off[i] = ch * kChunk + ((un ^ ((ch >> 1) & 3)) << 4);
+        }
+        auto issue = [&](uint32_t k) {
+            const uint32_t buf = stage_s + (k & 1) * kStageBytes;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + (((size_t)src_off16[i] + (size_t)k * 4) << 4);
+                cp_async16(buf + dst_off[i], src, k < src_nch[i] ? 16u : 0u);
+            }
+            cp_async_commit();
+        };
+
+        __syncwarp();  // previous task's readers are done with both buffers
+        if (kmax) issue(0);
+        for (uint32_t k = 0; k < kmax; k++) {
+            cp_async_wait_all();
+            __syncwarp();
+            if (k + 1 < kmax) issue(k + 1);
+            const uint8_t *buf = stage + (k & 1) * kStageBytes + lane * kChunk;
+            const int64_t relk = rel0 + (int64_t)k * kChunk;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t g = relk + j * 16;
+                if (valid && g == (int64_t)pos && g + 16 <= (int64_t)c.end) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(buf + ((j ^ my_swz) << 4));
+                    uint32_t t = fstep4<COLMODE>(s, w.x, ft);
+                    t = fstep4<COLMODE>(t, w.y, ft);
+                    t = fstep4<COLMODE>(t, w.z, ft);
+                    t = fstep4<COLMODE>(t, w.w, ft);
+                    if (t != H) {
+                        s = t;
+                        if (CP) {
+                            if (c.cp_pos == pos) {
+                                uint32_t nc = 16;
+                                if ((w.x | w.y | w.z | w.w) & 0x80808080u)
+                                    nc -= cont_bytes(w.x) + cont_bytes(w.y) + cont_bytes(w.z) + cont_bytes(w.w);
+                                c.cp_count += nc;
+                                c.cp_pos = pos + 16;
+                            } else {
+                                cp_catch_up(c, pos + 16);  // counting starts inside / after this group (chunk halo)
+                            }
+                        }
+                        pos += 16;
+                    } else {
+                        // something happened in these 16 bytes: redo them exactly
+                        c.state = s;
+                        c.at = pos;
+                        exact_scan<MODE, CP>(c, im, out, true, pos + 16, phase, H);
+                        s = c.state;
+                        pos = c.at;
+                        if (CP) cp_catch_up(c, pos);
+                    }
+                }
+            }
+        }
+        if (valid) {
+            // tail: whatever is left after the last full 16-byte group
+            c.state = s;
+            c.at = pos;
+            exact_scan<MODE, CP>(c, im, out, false, 0, 0, 0);
+            out.unit_counts[c.unit] = c.nemit;
+        }
+    }
+}
+
+}  // namespace acb

@@ -1,0 +1,360 @@
+"""Host-side mirror of the reference's Python API on top of the C ABI.
+
+Reference being mirrored: /root/reference/src/lib.rs (PyO3 classes
+``AhoCorasick`` 29-33/134-273, ``BytesAhoCorasick`` 360-435, enums 91-128) and
+pysrc/ahocorasick_rs/ahocorasick_rs.pyi.  Same names, argument meaning and
+error behaviour; the scan itself runs in the sm_100a kernels behind
+include/acb200.h.  There is no CPU fallback: without the CUDA library or a
+CUDA device every search raises.
+
+Additions next to the drop-in methods (the reference API is one haystack per
+call): ``find_matches_as_indexes_batch`` and ``scan_device`` for batches that
+are already device resident.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import threading
+from typing import Iterable, Optional, Sequence
+
+import numpy as np
+
+from . import _capi
+
+
+class MatchKind(enum.Enum):
+    """reference: src/lib.rs:92-98"""
+    Standard = 0
+    LeftmostFirst = 1
+    LeftmostLongest = 2
+
+
+class Implementation(enum.Enum):
+    """reference: src/lib.rs:111-118.  Here: device table layout hint only;
+    results are identical for every value (tests/test_ac.py:22-56)."""
+    NoncontiguousNFA = 0
+    ContiguousNFA = 1
+    DFA = 2
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda():
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise RuntimeError("ahocorasick_rs_b200 needs a CUDA device: the scan has no CPU fallback")
+    return torch
+
+
+class _Automaton:
+    """Owns the host automaton handle, its device image and a growable device
+    workspace.  Shared by both public classes."""
+
+    CHUNK_BYTES = 4096          # unit size for chunked overlapping scans of one large haystack
+    CHUNKED_MIN_BYTES = 1 << 16
+
+    def __init__(self, pattern_bytes: Sequence[bytes], matchkind: MatchKind, implementation: Optional[Implementation]):
+        L = _capi.lib()
+        n = len(pattern_bytes)
+        offs = np.zeros(n + 1, dtype=np.uint64)
+        if n:
+            np.cumsum(np.fromiter((len(p) for p in pattern_bytes), dtype=np.uint64, count=n), out=offs[1:])
+        blob = np.frombuffer(b"".join(pattern_bytes) or b"\0", dtype=np.uint8)
+        h = C.c_void_p()
+        impl = -1 if implementation is None else implementation.value
+        rc = L.acb_build(blob.ctypes.data, offs.ctypes.data, n, matchkind.value, impl, C.byref(h))
+        if rc != _capi.ACB_OK:
+            raise ValueError(_capi.last_error())
+        self._h = h
+        self._L = L
+        self.matchkind = matchkind
+        self.n_patterns = n
+        self.num_states = int(L.acb_num_states(h))
+        self.num_columns = int(L.acb_num_columns(h))
+        self.max_pattern_len = int(L.acb_max_pattern_len(h))
+        self._images = {}      # device index -> uint8 tensor
+        self._ws = {}          # device index -> dict of tensors
+        self._lock = threading.Lock()
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._L.acb_free(h)
+            self._h = None
+
+    # ---- device residency ---------------------------------------------------
+    def image(self, device):
+        """The flat tables on `device` (uploaded once, then cached)."""
+        torch = _require_cuda()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        img = self._images.get(idx)
+        if img is None:
+            nbytes = int(self._L.acb_image_bytes(self._h))
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            rc = self._L.acb_image_write(self._h, host.data_ptr(), nbytes)
+            if rc != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            img = host.to(torch.device("cuda", idx), non_blocking=False)
+            self._images[idx] = img
+        return img
+
+    def _workspace(self, device, n_units: int, capacity: int):
+        torch = _torch()
+        idx = device.index
+        ws = self._ws.get(idx)
+        if ws is None or ws["n_units"] < n_units or ws["capacity"] < capacity:
+            n_alloc = max(n_units, ws["n_units"] if ws else 0, 1)
+            cap = max(capacity, ws["capacity"] if ws else 0, 1024)
+            dev = torch.device("cuda", idx)
+            ws = {
+                "n_units": n_alloc, "capacity": cap,
+                "raw": torch.empty((cap, 4), dtype=torch.int32, device=dev),
+                "raw_seq": torch.empty(cap, dtype=torch.int32, device=dev),
+                "raw_unit": torch.empty(cap, dtype=torch.int32, device=dev),
+                "unit_counts": torch.empty(n_alloc, dtype=torch.int32, device=dev),
+                "unit_offsets": torch.empty(n_alloc + 1, dtype=torch.int64, device=dev),
+                "scratch": torch.empty(int(self._L.acb_scratch_words(n_alloc)), dtype=torch.int64, device=dev),
+                "total": torch.zeros(2, dtype=torch.int64, device=dev),
+                "out": torch.empty((cap, 4), dtype=torch.int32, device=dev),
+            }
+            self._ws[idx] = ws
+        return ws
+
+    def _ws_struct(self, ws):
+        s = _capi.Workspace()
+        s.dev_raw = ws["raw"].data_ptr()
+        s.dev_raw_seq = ws["raw_seq"].data_ptr()
+        s.dev_raw_unit = ws["raw_unit"].data_ptr()
+        s.raw_capacity = ws["capacity"]
+        s.dev_unit_counts = ws["unit_counts"].data_ptr()
+        s.dev_unit_offsets = ws["unit_offsets"].data_ptr()
+        s.dev_scratch = ws["scratch"].data_ptr()
+        s.dev_total = ws["total"].data_ptr()
+        s.dev_out = ws["out"].data_ptr()
+        s.out_capacity = ws["capacity"]
+        return s
+
+    def check_overlapping(self, overlapping: bool):
+        # reference: the iterator is refused before any byte is read (src/lib.rs:52-54, 36-39)
+        if overlapping and self.matchkind != MatchKind.Standard:
+            raise ValueError(f"match kind {self.matchkind.name} does not support overlapping searches")
+
+    # ---- scans ------------------------------------------------------------------
+    def scan_device(self, data, offsets, overlapping=False, codepoints=False, capacity: Optional[int] = None,
+                    sync: bool = True):
+        """Scan a device-resident batch.  data: uint8 CUDA tensor, offsets: int64
+        CUDA tensor (n+1).  Returns (matches, match_offsets, total): matches is an
+        int32 CUDA tensor (total, 4) = (haystack, pattern, start, end) in the
+        reference's order, match_offsets (n+1) brackets each haystack's rows.
+        With sync=False the call returns right after enqueueing (total is a
+        device tensor and matches is the whole capacity-sized buffer)."""
+        torch = _require_cuda()
+        self.check_overlapping(overlapping)
+        dev = data.device
+        n = offsets.numel() - 1
+        img = self.image(dev)
+        cap = capacity or max(1024, n * 2)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with self._lock, torch.cuda.device(dev):
+            while True:
+                ws = self._workspace(dev, n, cap)
+                st = self._ws_struct(ws)
+                rc = self._L.acb_scan_batch(self._h, img.data_ptr(), data.data_ptr(), offsets.data_ptr(), n,
+                                            int(bool(overlapping)), int(bool(codepoints)), C.byref(st), stream)
+                if rc != _capi.ACB_OK:
+                    err = _capi.last_error()
+                    raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
+                if not sync:
+                    return ws["out"], ws["unit_offsets"][: n + 1], ws["total"]
+                total = int(ws["total"][0].item())
+                if total <= ws["capacity"]:
+                    return ws["out"][:total], ws["unit_offsets"][: n + 1], total
+                cap = total + total // 8 + 16
+
+    def scan_chunked_device(self, data, codepoints=False, chunk_bytes: Optional[int] = None):
+        """Overlapping scan of ONE device-resident haystack, chunk-parallel."""
+        torch = _require_cuda()
+        self.check_overlapping(True)
+        dev = data.device
+        chunk = chunk_bytes or self.CHUNK_BYTES
+        n_units = int(self._L.acb_chunk_count(data.numel(), chunk))
+        img = self.image(dev)
+        cap = max(1024, n_units)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with self._lock, torch.cuda.device(dev):
+            while True:
+                ws = self._workspace(dev, n_units, cap)
+                st = self._ws_struct(ws)
+                rc = self._L.acb_scan_chunked(self._h, img.data_ptr(), data.data_ptr(), data.numel(), chunk,
+                                              int(bool(codepoints)), C.byref(st), stream)
+                if rc != _capi.ACB_OK:
+                    err = _capi.last_error()
+                    raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
+                total = int(ws["total"][0].item())
+                if total <= ws["capacity"]:
+                    return ws["out"][:total], total
+                cap = total + total // 8 + 16
+
+    def scan_host_batch(self, chunks: Sequence[bytes], overlapping: bool, codepoints: bool):
+        """Host buffers in, host numpy out: (matches uint32 (k,4), match_offsets int64 (n+1))."""
+        torch = _require_cuda()
+        self.check_overlapping(overlapping)
+        n = len(chunks)
+        lens = np.fromiter((len(c) for c in chunks), dtype=np.int64, count=n)
+        offs = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        total_bytes = int(offs[-1])
+        if total_bytes >= (1 << 32) - 1 and n == 1:
+            raise ValueError("haystacks of 4 GiB and more are not supported yet")
+        dev = torch.device("cuda", torch.cuda.current_device())
+        host = torch.empty(max(total_bytes, 1), dtype=torch.uint8, pin_memory=True)
+        hv = host.numpy()
+        pos = 0
+        for c in chunks:
+            ln = len(c)
+            hv[pos:pos + ln] = np.frombuffer(c, dtype=np.uint8)
+            pos += ln
+        d_data = host.to(dev, non_blocking=True)
+        if n == 1 and overlapping and total_bytes >= self.CHUNKED_MIN_BYTES:
+            m, total = self.scan_chunked_device(d_data[:total_bytes], codepoints)
+            return m.cpu().numpy().view(np.uint32), np.array([0, total], dtype=np.int64)
+        d_offs = torch.from_numpy(offs).to(dev, non_blocking=True)
+        m, moffs, _ = self.scan_device(d_data, d_offs, overlapping, codepoints)
+        return m.cpu().numpy().view(np.uint32), moffs.cpu().numpy()
+
+
+def _as_buffer_bytes(obj) -> bytes:
+    """reference PyBufferBytes::try_from (src/lib.rs:281-302): 1-D, C-contiguous u8 buffer."""
+    if isinstance(obj, str):
+        raise TypeError("a bytes-like object is required, not 'str'")
+    try:
+        mv = memoryview(obj)
+    except TypeError as e:
+        raise TypeError(str(e)) from None
+    if mv.ndim > 1:
+        raise TypeError("Only one-dimensional sequences are supported")
+    if not mv.c_contiguous:
+        raise TypeError("Must be a contiguous sequence of bytes")
+    if mv.itemsize != 1 or mv.format not in ("B", "b", "c"):
+        raise BufferError("buffer contents are not compatible with u8")
+    return mv.tobytes() if not isinstance(obj, bytes) else obj
+
+
+def _tuples(m: np.ndarray):
+    return list(zip(m[:, 1].tolist(), m[:, 2].tolist(), m[:, 3].tolist()))
+
+
+class AhoCorasick:
+    """Search for multiple pattern strings against a haystack string
+    (reference: src/lib.rs:15-33, 134-273).
+
+    * ``patterns``: any iterable of non-empty ``str``.
+    * ``matchkind``: ``MatchKind.Standard`` (default), ``LeftmostFirst`` or ``LeftmostLongest``.
+    * ``store_patterns``: keep references to the patterns to speed up
+      ``find_matches_as_strings``; ``None`` = store iff total length <= 4096 code points.
+    * ``implementation``: ``Implementation`` hint or ``None``.
+    """
+
+    def __init__(self, patterns: Iterable[str], matchkind: MatchKind = MatchKind.Standard,
+                 store_patterns: Optional[bool] = None, implementation: Optional[Implementation] = None):
+        if not isinstance(matchkind, MatchKind):
+            raise TypeError("matchkind must be a MatchKind")
+        if implementation is not None and not isinstance(implementation, Implementation):
+            raise TypeError("implementation must be an Implementation or None")
+        it = iter(patterns)  # TypeError for non-iterables, like try_iter()? at src/lib.rs:147
+        strs = []
+        encoded = []
+        total = 0
+        decide = store_patterns is None
+        store = True if decide else bool(store_patterns)
+        for p in it:
+            if not isinstance(p, str):
+                raise TypeError(f"'{type(p).__name__}' object cannot be converted to 'PyString'")
+            if p == "":
+                raise ValueError("You passed in an empty string as a pattern")
+            try:
+                b = p.encode("utf-8")
+            except UnicodeEncodeError:
+                break  # reference quirk: a pattern that is not valid UTF-8 silently ends ingestion (src/lib.rs:200-203)
+            if decide and store:
+                total += len(p)
+                if total > 4096:
+                    store = False
+                    strs = []
+            if store:
+                strs.append(p)
+            encoded.append(b)
+        self._patterns = strs if store else None
+        self._ac = _Automaton(encoded, matchkind, implementation)
+
+    def find_matches_as_indexes(self, haystack: str, overlapping: bool = False):
+        """-> list of (pattern index, start, end) in code points (src/lib.rs:229-249)."""
+        if not isinstance(haystack, str):
+            raise TypeError("argument 'haystack': 'str' expected")
+        self._ac.check_overlapping(overlapping)
+        m, _ = self._ac.scan_host_batch([haystack.encode("utf-8")], overlapping, codepoints=True)
+        return _tuples(m)
+
+    def find_matches_as_strings(self, haystack: str, overlapping: bool = False):
+        """-> list of matched patterns (src/lib.rs:253-272)."""
+        if not isinstance(haystack, str):
+            raise TypeError("argument 'haystack': 'str' expected")
+        self._ac.check_overlapping(overlapping)
+        m, _ = self._ac.scan_host_batch([haystack.encode("utf-8")], overlapping, codepoints=True)
+        if self._patterns is not None:
+            pats = self._patterns
+            return [pats[i] for i in m[:, 1].tolist()]
+        return [haystack[s:e] for s, e in zip(m[:, 2].tolist(), m[:, 3].tolist())]
+
+    # ---- additions: batches ------------------------------------------------------
+    def find_matches_as_indexes_batch(self, haystacks: Sequence[str], overlapping: bool = False):
+        """One list of (pattern, start, end) per haystack, each exactly what
+        ``find_matches_as_indexes`` returns for it."""
+        self._ac.check_overlapping(overlapping)
+        m, offs = self._ac.scan_host_batch([h.encode("utf-8") for h in haystacks], overlapping, codepoints=True)
+        t = _tuples(m)
+        return [t[offs[i]:offs[i + 1]] for i in range(len(haystacks))]
+
+    def scan_device(self, data, offsets, overlapping: bool = False, **kw):
+        """Device-resident UTF-8 batch -> (matches, match_offsets, total); code point indexes."""
+        return self._ac.scan_device(data, offsets, overlapping, codepoints=True, **kw)
+
+
+class BytesAhoCorasick:
+    """Search for multiple pattern bytes against a bytes-like haystack
+    (reference: src/lib.rs:342-363, 366-435).  No references to the patterns are kept."""
+
+    def __init__(self, patterns: Iterable, matchkind: MatchKind = MatchKind.Standard,
+                 implementation: Optional[Implementation] = None):
+        if not isinstance(matchkind, MatchKind):
+            raise TypeError("matchkind must be a MatchKind")
+        if implementation is not None and not isinstance(implementation, Implementation):
+            raise TypeError("implementation must be an Implementation or None")
+        encoded = []
+        for p in iter(patterns):
+            b = _as_buffer_bytes(p)
+            if len(b) == 0:
+                raise ValueError("You passed in an empty pattern")
+            encoded.append(b)
+        self._ac = _Automaton(encoded, matchkind, implementation)
+
+    def find_matches_as_indexes(self, haystack, overlapping: bool = False):
+        """-> list of (pattern index, start, end) in byte offsets (src/lib.rs:422-434)."""
+        hay = _as_buffer_bytes(haystack)
+        self._ac.check_overlapping(overlapping)
+        m, _ = self._ac.scan_host_batch([hay], overlapping, codepoints=False)
+        return _tuples(m)
+
+    def find_matches_as_indexes_batch(self, haystacks: Sequence, overlapping: bool = False):
+        self._ac.check_overlapping(overlapping)
+        m, offs = self._ac.scan_host_batch([_as_buffer_bytes(h) for h in haystacks], overlapping, codepoints=False)
+        t = _tuples(m)
+        return [t[offs[i]:offs[i + 1]] for i in range(len(haystacks))]
+
+    def scan_device(self, data, offsets, overlapping: bool = False, **kw):
+        """Device-resident batch -> (matches, match_offsets, total); byte offsets."""
+        return self._ac.scan_device(data, offsets, overlapping, codepoints=False, **kw)

@@ -1,0 +1,78 @@
+"""Multi-GPU: one process per GPU, haystack batches sharded by contiguous index
+ranges, the table replicated, no data-path collective during the scan.  The
+only exchange is the gather of per-shard match lists (torch.distributed: NCCL
+over NVLink on GPUs, gloo in the CPU tests); concatenation in rank order is
+already the reference's order.
+
+The reference has nothing like this (one haystack per call, one core); the
+semantics being preserved are simply "the batch result equals the per-haystack
+results in haystack order"."""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+
+def partition_by_bytes(offsets: np.ndarray, world: int) -> List[Tuple[int, int]]:
+    """Split haystacks [0, n) into `world` contiguous ranges with ~equal bytes.
+    Returns [(lo, hi)] per rank (possibly empty ranges)."""
+    n = len(offsets) - 1
+    base = int(offsets[0])
+    total = int(offsets[-1]) - base
+    cuts = [0]
+    for r in range(1, world):
+        target = base + (total * r) // world
+        # first haystack whose start is >= target
+        idx = int(np.searchsorted(offsets[: n + 1], target, side="left"))
+        cuts.append(min(max(idx, cuts[-1]), n))
+    cuts.append(n)
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]
+
+
+def gather_match_lists(local, hay_base: int, group=None, dst: Optional[int] = None):
+    """local: (k, 4) int32 tensor (haystack, pattern, start, end) with shard-local
+    haystack ids.  Returns the global list (haystack ids rebased by each rank's
+    hay_base) on every rank (dst=None) or on rank `dst` only (others get None).
+    Two collectives: all_gather of the counts, then a padded all_gather."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    dev = local.device
+    meta = torch.tensor([local.shape[0], hay_base], dtype=torch.int64, device=dev)
+    metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(metas, meta, group=group)
+    metas = metas.view(world, 2)
+    counts = metas[:, 0].tolist()
+    bases = metas[:, 1].tolist()
+    kmax = max(max(counts), 1)
+    padded = torch.zeros((kmax, 4), dtype=torch.int32, device=dev)
+    padded[: local.shape[0]] = local
+    everything = torch.empty(world * kmax * 4, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(everything, padded.view(-1), group=group)
+    everything = everything.view(world * kmax, 4)
+    if dst is not None and rank != dst:
+        return None
+    parts = []
+    for r in range(world):
+        part = everything[r * kmax: r * kmax + counts[r]].clone()
+        part[:, 0] += int(bases[r])
+        parts.append(part)
+    return torch.cat(parts, dim=0)
+
+
+def scan_sharded(scan_fn: Callable, data: np.ndarray, offsets: np.ndarray, group=None, device=None):
+    """Every rank holds the whole host batch (tests / small inputs): scan my
+    shard with scan_fn(data_shard, offsets_shard) -> (k,4) int32 tensor on
+    `device`, then gather.  Returns the full ordered match list on every rank."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    lo, hi = partition_by_bytes(offsets, world)[rank]
+    sub_offs = offsets[lo: hi + 1] - offsets[lo]
+    sub_data = data[offsets[lo]: offsets[hi]]
+    local = scan_fn(sub_data, sub_offs.astype(np.int64))
+    return gather_match_lists(local, lo, group=group)

@@ -1,0 +1,175 @@
+/*
+ * acb200.h -- C ABI of the B200-native multi-pattern matcher (libacb200.so).
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference
+ * (G-Research/ahocorasick_rs) has no C ABI of its own: its PyO3 shim
+ * (src/lib.rs) calls straight into the Rust crate `aho-corasick` 1.1.4.  Each
+ * entry point below names the reference call site it stands in for; a
+ * maintainer of the reference would bind these from src/lib.rs through
+ * `extern "C"` or, as this repo does, from Python with
+ * ctypes (ahocorasick_rs_b200/_capi.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - every function returns ACB_OK (0) or a negative ACB_E* code; text for the
+ *     last error on the calling thread comes from acb_last_error();
+ *   - "dev_" pointers are CUDA device pointers on the current device; the
+ *     library never allocates device memory: the caller (PyTorch's caching
+ *     allocator in this repo) owns every buffer and says how big it is;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *     and nothing synchronises unless stated;
+ *   - there is no CPU fallback: scan entry points fail with ACB_ECUDA when no
+ *     device is usable.
+ */
+#ifndef ACB200_H
+#define ACB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ACB_OK 0
+#define ACB_EINVAL (-1)      /* bad argument */
+#define ACB_EBUILD (-2)      /* automaton construction failed (reference: BuildError -> ValueError, src/lib.rs:215,406) */
+#define ACB_EUNSUPPORTED (-3) /* overlapping search on a non-Standard automaton (reference: MatchError -> ValueError, src/lib.rs:36-39,52-54) */
+#define ACB_ECUDA (-4)       /* CUDA runtime error / no device */
+#define ACB_ECAPACITY (-5)   /* a caller-provided buffer is too small */
+
+/* MatchKind (reference: src/lib.rs:92-98) */
+#define ACB_STANDARD 0
+#define ACB_LEFTMOST_FIRST 1
+#define ACB_LEFTMOST_LONGEST 2
+
+/* Implementation (reference: src/lib.rs:111-118). -1 = None (heuristic).
+ * Here it selects the device table layout only; results never depend on it. */
+#define ACB_IMPL_AUTO (-1)
+#define ACB_IMPL_NONCONTIGUOUS_NFA 0
+#define ACB_IMPL_CONTIGUOUS_NFA 1
+#define ACB_IMPL_DFA 2
+
+typedef struct acb_automaton acb_automaton;
+
+/* One match, as the reference's (pattern, start, end) tuple (src/lib.rs:240-246,
+ * 431) plus the haystack it belongs to.  16 bytes, written with one store. */
+typedef struct acb_match {
+    uint32_t haystack; /* index into the batch (0 for single-haystack calls) */
+    uint32_t pattern;  /* index into the pattern list given to acb_build */
+    uint32_t start;    /* byte offset, or code point index when codepoints != 0 */
+    uint32_t end;      /* exclusive */
+} acb_match;
+
+const char *acb_last_error(void);
+const char *acb_version(void);
+
+/*
+ * Build an automaton on the host.
+ * Stands in for AhoCorasickBuilder::new().kind(..).match_kind(..).build(..)
+ * at src/lib.rs:186-215 (str) and 401-406 (bytes).
+ * Pattern i is blob[offsets[i] .. offsets[i+1]); ids are input order.  Empty
+ * patterns are an error here too (the reference rejects them before the crate
+ * sees them, src/lib.rs:204-207,386-389).
+ */
+int acb_build(const uint8_t *blob, const uint64_t *offsets, uint64_t n_patterns, int match_kind,
+              int implementation, acb_automaton **out);
+void acb_free(acb_automaton *a);
+
+/* Facts about a built automaton. */
+uint64_t acb_num_patterns(const acb_automaton *a);
+uint64_t acb_num_states(const acb_automaton *a);
+uint32_t acb_num_columns(const acb_automaton *a);
+uint32_t acb_max_pattern_len(const acb_automaton *a);
+uint32_t acb_min_pattern_len(const acb_automaton *a);
+int acb_match_kind(const acb_automaton *a);
+
+/*
+ * The device image: the flat tables the kernels read (column map, dense
+ * transition rows, per-state match lists, pattern lengths), serialised into
+ * one buffer.  The caller allocates acb_image_bytes() on the device, fills it
+ * from acb_image_write()'s host copy ("table uploaded once to HBM"), and
+ * passes it to every scan.
+ */
+uint64_t acb_image_bytes(const acb_automaton *a);
+int acb_image_write(const acb_automaton *a, void *host_dst, uint64_t dst_bytes);
+
+/*
+ * Caller-provided device workspace for one scan.  n_units = number of scan
+ * units: haystacks for acb_scan_batch, chunks for acb_scan_chunked
+ * (acb_chunk_count()).
+ */
+typedef struct acb_workspace {
+    acb_match *dev_raw;      /* [raw_capacity] unordered matches as kernels emit them */
+    uint32_t *dev_raw_seq;   /* [raw_capacity] rank of each raw match inside its unit */
+    uint32_t *dev_raw_unit;  /* [raw_capacity] unit each raw match belongs to */
+    uint64_t raw_capacity;
+    uint32_t *dev_unit_counts;  /* [n_units] matches per unit (output) */
+    uint64_t *dev_unit_offsets; /* [n_units + 1] exclusive prefix sum of the counts (output) */
+    uint64_t *dev_scratch;      /* [acb_scratch_words(n_units)] */
+    uint64_t *dev_total;        /* [2]: [0] = matches found, [1] = matches written to dev_out */
+    acb_match *dev_out;         /* [out_capacity] final matches in the reference's order */
+    uint64_t out_capacity;
+} acb_workspace;
+
+uint64_t acb_scratch_words(uint64_t n_units);
+
+/*
+ * Scan a batch of haystacks resident in device memory:
+ * haystack h = dev_bytes[dev_offsets[h] .. dev_offsets[h+1]).
+ *
+ * Per haystack this is the drain of the reference's iterator: get_matches
+ * (src/lib.rs:42-68) choosing try_find_iter (58-60) or
+ * try_find_overlapping_iter (52-54), collected at 238-248 (str) / 433 (bytes).
+ * codepoints != 0 reports start/end as code point indexes, i.e. it also does
+ * the work of get_byte_to_code_point (src/lib.rs:73-88) for valid UTF-8.
+ *
+ * On return (after the stream has run): ws->dev_out holds
+ * min(total, out_capacity) matches ordered by haystack and then in the
+ * reference's iteration order; ws->dev_unit_offsets[h..h+1] brackets haystack
+ * h's matches; ws->dev_total[0] is the true total.  If total exceeds
+ * raw_capacity or out_capacity nothing is lost silently: dev_total[0] says how
+ * much room a second call needs.
+ * overlapping on a non-Standard automaton returns ACB_EUNSUPPORTED before any
+ * byte is read, like the reference.
+ */
+int acb_scan_batch(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes,
+                   const int64_t *dev_offsets, int64_t n_haystacks, int overlapping, int codepoints,
+                   const acb_workspace *ws, void *stream);
+
+/*
+ * Scan ONE large device-resident haystack, split into fixed-size chunks that
+ * are scanned in parallel.  overlapping must be non-zero (position-local, so
+ * chunking with a halo of max_pattern_len-1 bytes is exact); the serial
+ * restart rule of non-overlapping search is served by acb_scan_batch with
+ * n_haystacks = 1.  Output order = the reference's (end, start, pattern).
+ * Units are chunks: acb_chunk_count(len, chunk_bytes).
+ */
+uint64_t acb_chunk_count(uint64_t len, uint32_t chunk_bytes);
+int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, uint64_t len,
+                     uint32_t chunk_bytes, int codepoints, const acb_workspace *ws, void *stream);
+
+/* Kernel launch bookkeeping for bench.py's "gpu_launches". */
+uint64_t acb_launch_count(void);
+
+/*
+ * Device-side timing of the scan kernel alone (CUDA events recorded on the
+ * caller's stream around the scan kernel of every subsequent scan call), for
+ * the roofline figure.  acb_timing_read synchronises on the recorded events,
+ * returns their summed duration and count, and clears them.
+ */
+int acb_timing_enable(int on);
+int acb_timing_read(double *total_ms, uint64_t *n_scans);
+
+/* Tuning knobs (0 = library default). Affects speed only, never results. */
+typedef struct acb_tuning {
+    int kernel;        /* 0 auto, 1 = plain (table in global/L2), 2 = staged (hot rows in shared memory) */
+    int hot_rows;      /* cap on rows kept in shared memory */
+    int ctas_per_sm;   /* persistent grid = ctas_per_sm * SM count */
+} acb_tuning;
+int acb_set_tuning(const acb_tuning *t);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACB200_H */

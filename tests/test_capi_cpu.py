@@ -1,0 +1,117 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/acb200.h
+declares; host-side API behaviour that needs no GPU (construction, argument
+and error handling mirrored from the reference's tests)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ahocorasick_rs_b200 import (AhoCorasick, BytesAhoCorasick, Implementation, MatchKind, MATCHKIND_STANDARD,
+                                 MATCHKIND_LEFTMOST_FIRST, MATCHKIND_LEFTMOST_LONGEST, _capi)
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "acb200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(acb_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 18
+    L = _capi.lib()
+    for name in declared:
+        assert getattr(L, name) is not None, name
+    assert declared == set(_capi.EXPORTS)
+    assert b"sm_100a" in L.acb_version()
+
+
+def test_build_and_image_roundtrip_without_gpu():
+    L = _capi.lib()
+    pats = [b"hello", b"world", b"fish"]
+    offs = np.array([0, 5, 10, 14], dtype=np.uint64)
+    blob = np.frombuffer(b"".join(pats), dtype=np.uint8)
+    h = C.c_void_p()
+    assert L.acb_build(blob.ctypes.data, offs.ctypes.data, 3, 0, -1, C.byref(h)) == 0
+    assert L.acb_num_patterns(h) == 3 and L.acb_max_pattern_len(h) == 5 and L.acb_min_pattern_len(h) == 4
+    assert L.acb_num_states(h) == 2 + 14
+    n = L.acb_image_bytes(h)
+    buf = np.zeros(n, dtype=np.uint8)
+    assert L.acb_image_write(h, buf.ctypes.data, n - 1) == _capi.ACB_ECAPACITY
+    assert L.acb_image_write(h, buf.ctypes.data, n) == 0
+    L.acb_free(h)
+    bad = np.array([0, 5, 5, 14], dtype=np.uint64)  # an empty pattern
+    assert L.acb_build(blob.ctypes.data, bad.ctypes.data, 3, 0, -1, C.byref(h)) == _capi.ACB_EBUILD
+    assert b"empty pattern" in L.acb_last_error()
+    assert L.acb_scratch_words(100_000) > 100_000
+    assert L.acb_chunk_count(10_000, 4096) == 3
+
+
+def test_constructor_errors_like_the_reference():
+    # reference tests/test_ac.py:75-83, 157-168; tests/test_ac_bytes.py:118-130, 164-172
+    with pytest.raises(TypeError):
+        AhoCorasick(None)
+    with pytest.raises(TypeError):
+        AhoCorasick(["x", 12])
+    for bad in ([""], ["", "xx"], ["xx", ""]):
+        for sp in (True, False):
+            with pytest.raises(ValueError) as e:
+                AhoCorasick(bad, store_patterns=sp)
+            assert "You passed in an empty string as a pattern" in str(e.value)
+    with pytest.raises(TypeError):
+        BytesAhoCorasick(None)
+    with pytest.raises(TypeError):
+        BytesAhoCorasick([b"x", 12])
+    with pytest.raises(TypeError):
+        BytesAhoCorasick([b"x", "y"])
+    for bad in ([b""], [b"", b"xx"], [b"xx", b""]):
+        with pytest.raises(ValueError) as e:
+            BytesAhoCorasick(bad)
+        assert "You passed in an empty pattern" in str(e.value)
+    with pytest.raises(TypeError):
+        BytesAhoCorasick([np.zeros((2, 2), dtype=np.uint8)])  # more than one dimension
+    with pytest.raises(TypeError):
+        BytesAhoCorasick([np.arange(10, dtype=np.uint8)[::2]])  # not contiguous
+    # iterables and buffer types are accepted
+    AhoCorasick(iter(["hello", "world"]))
+    AhoCorasick(p for p in ["a", "b"])
+    BytesAhoCorasick([memoryview(b"hello"), bytearray(b"world")])
+
+
+def test_enums_and_deprecated_constants():
+    assert MATCHKIND_STANDARD == MatchKind.Standard
+    assert MATCHKIND_LEFTMOST_FIRST == MatchKind.LeftmostFirst
+    assert MATCHKIND_LEFTMOST_LONGEST == MatchKind.LeftmostLongest
+    assert MatchKind.Standard != MatchKind.LeftmostFirst
+    assert {i.name for i in Implementation} == {"NoncontiguousNFA", "ContiguousNFA", "DFA"}
+    import ahocorasick_rs
+    assert ahocorasick_rs.AhoCorasick is AhoCorasick and ahocorasick_rs.MATCHKIND_STANDARD == MatchKind.Standard
+
+
+def test_store_patterns_heuristic():
+    # reference src/lib.rs:162-184: store iff the running total of code points stays <= 4096
+    assert AhoCorasick(["a" * 4096])._patterns is not None
+    assert AhoCorasick(["a" * 4097])._patterns is None
+    assert AhoCorasick(["a" * 4000, "b" * 97])._patterns is None
+    assert AhoCorasick(["é" * 4096])._patterns is not None  # code points, not bytes
+    assert AhoCorasick(["a" * 5000], store_patterns=True)._patterns is not None
+    assert AhoCorasick(["a"], store_patterns=False)._patterns is None
+
+
+def test_overlapping_refused_before_any_work_and_no_cpu_fallback():
+    ac = AhoCorasick(["a"], matchkind=MatchKind.LeftmostFirst)
+    with pytest.raises(ValueError):
+        ac.find_matches_as_indexes("", overlapping=True)
+    with pytest.raises(ValueError):
+        BytesAhoCorasick([b"a"], matchkind=MatchKind.LeftmostLongest).find_matches_as_indexes(b"", overlapping=True)
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):  # fails loudly: no silent CPU path
+            AhoCorasick(["a"]).find_matches_as_indexes("abc")
+
+
+def test_many_patterns_construction():
+    # reference tests/test_ac.py:86-100 exercises > 10 240 patterns (chunked ingestion)
+    pats = [f"p{i}_{i * 7919 % 1000}_" for i in range(30_000)]
+    ac = AhoCorasick(pats)
+    assert ac._ac.n_patterns == 30_000 and ac._patterns is None

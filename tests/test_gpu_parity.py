@@ -1,0 +1,209 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI
+(include/acb200.h) by the package, against the CPU oracle on the same seeded
+inputs, against the reference's golden vectors, and -- at larger sizes --
+through size-independent properties.  Bit-exact: integer/index work."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from ahocorasick_rs_b200 import (AhoCorasick, BytesAhoCorasick, Implementation, MatchKind, _capi, workloads as W)
+from oracle import Oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+KINDS = [MatchKind.Standard, MatchKind.LeftmostFirst, MatchKind.LeftmostLongest]
+
+with open(os.path.join(HERE, "golden", "reference_vectors.json"), encoding="utf-8") as f:
+    VECTORS = json.load(f)["vectors"]
+
+
+def set_kernel(kernel=0, hot_rows=0):
+    t = _capi.Tuning(kernel, hot_rows, 0)
+    assert _capi.lib().acb_set_tuning(C.byref(t)) == 0
+
+
+@pytest.fixture(params=["staged", "plain", "staged-tiny-hot"])
+def kernel(request):
+    if request.param == "plain":
+        set_kernel(1)
+    elif request.param == "staged":
+        set_kernel(2)
+    else:
+        set_kernel(2, 5)  # 5 hot rows: nearly every group traps, exercising the exact/fast hand-over
+    yield request.param
+    set_kernel(0)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_batch(ac, data, offs, overlapping=False):
+    m, moffs, total = ac.scan_device(dev(data), dev(offs), overlapping)
+    return m.cpu().numpy().view(np.uint32), moffs.cpu().numpy(), total
+
+
+def check_batch(pats_bytes, kind, data, offs, overlapping=False, codepoints=False, implementation=None):
+    orc = Oracle(pats_bytes, kind.name)
+    total, counts, rec = orc.scan_batch(data, offs, overlapping=overlapping, codepoints=codepoints)
+    if codepoints:
+        ac = AhoCorasick([p.decode() for p in pats_bytes], kind, implementation=implementation)
+    else:
+        ac = BytesAhoCorasick(pats_bytes, kind, implementation=implementation)
+    m, moffs, gtotal = gpu_batch(ac, data, offs, overlapping)
+    assert gtotal == total
+    assert np.array_equal(np.diff(moffs), counts.astype(np.int64))
+    assert np.array_equal(m, rec)
+    return total
+
+
+# ---------------------------------------------------------------- golden vectors, through the drop-in classes
+@pytest.mark.parametrize("vec", VECTORS, ids=[f"{i}:{v['src']}" for i, v in enumerate(VECTORS)])
+def test_reference_vectors(vec, kernel):
+    kind = MatchKind[vec["kind"]]
+    hay = vec["haystack"]
+    if vec["cls"] == "str":
+        ac = AhoCorasick(vec["patterns"], matchkind=kind)
+        if vec.get("error"):
+            with pytest.raises(ValueError):
+                ac.find_matches_as_indexes(hay, overlapping=True)
+            with pytest.raises(ValueError):
+                ac.find_matches_as_strings(hay, overlapping=True)
+            return
+        idx = ac.find_matches_as_indexes(hay, overlapping=vec["overlapping"])
+        if "expect_strings" in vec:
+            assert [hay[s:e] for (_, s, e) in idx] == vec["expect_strings"]
+            assert ac.find_matches_as_strings(hay, overlapping=vec["overlapping"]) == vec["expect_strings"]
+    else:
+        raw = hay.encode()
+        ac = BytesAhoCorasick([p.encode() for p in vec["patterns"]], matchkind=kind)
+        if vec.get("error"):
+            with pytest.raises(ValueError):
+                ac.find_matches_as_indexes(raw, overlapping=True)
+            return
+        idx = ac.find_matches_as_indexes(raw, overlapping=vec["overlapping"])
+        if "expect_strings" in vec:
+            assert [raw[s:e].decode() for (_, s, e) in idx] == vec["expect_strings"]
+    if "expect_indexes" in vec:
+        assert [list(t) for t in idx] == vec["expect_indexes"]
+    assert all(isinstance(x, int) for t in idx for x in t)
+
+
+# ---------------------------------------------------------------- seeded batches vs the oracle
+@pytest.mark.parametrize("kind", KINDS, ids=lambda k: k.name)
+def test_ragged_small_alphabet(kind, kernel):
+    rng = np.random.default_rng(11)
+    pats = sorted({bytes(rng.integers(97, 100, size=rng.integers(1, 6)).astype(np.uint8)) for _ in range(40)})
+    pats += pats[:3]  # duplicates: distinct ids, same string
+    data, offs = W.ragged(3000, 300, b"abc", seed=12)
+    n = check_batch(pats, kind, data, offs)
+    assert n > 1000
+    if kind == MatchKind.Standard:
+        check_batch(pats, kind, data, offs, overlapping=True)
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=lambda k: k.name)
+def test_config2_shape_scaled(kind, kernel):
+    pats, data, offs = W.config2(1500)
+    n = check_batch([p.encode() for p in pats], kind, data, offs, codepoints=True, implementation=Implementation.DFA)
+    assert n > 50
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=lambda k: k.name)
+def test_config3_shape_scaled(kind, kernel):
+    pats, data, offs = W.config3(n_patterns=2000, n_lines=4000)
+    n = check_batch(pats, kind, data, offs)
+    assert n > 1000
+
+
+def test_config5_shape_scaled(kernel):
+    pats, data, offs = W.config5(n_patterns=20000, n_haystacks=512, hay_bytes=4096)
+    check_batch(pats, MatchKind.Standard, data, offs)
+
+
+def test_config4_shape_scaled_chunked_overlapping(kernel):
+    pats, data = W.config4(n_patterns=20000, hay_bytes=3_000_017)
+    orc = Oracle(pats, "Standard")
+    exp = orc.find(data.tobytes(), overlapping=True)
+    ac = BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA)
+    for chunk in (4096, 1000):
+        m, total = ac._ac.scan_chunked_device(dev(data), chunk_bytes=chunk)
+        got = m.cpu().numpy().view(np.uint32)
+        assert total == len(exp)
+        assert [tuple(int(x) for x in r[1:]) for r in got] == exp
+    # the drop-in call takes the same path for a large haystack
+    assert ac.find_matches_as_indexes(data.tobytes(), overlapping=True) == exp
+
+
+def test_unaligned_base_and_tiny_haystacks(kernel):
+    pats = [b"ab", b"b", b"abab", b"ba"]
+    rng = np.random.default_rng(5)
+    body = rng.integers(97, 99, size=5000, dtype=np.uint8).astype(np.uint8)
+    for shift in (1, 7, 33):
+        lens = rng.integers(0, 40, size=200)
+        offs = np.zeros(201, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        offs += shift
+        for kind in KINDS:
+            orc = Oracle(pats, kind.name)
+            total, counts, rec = orc.scan_batch(body, offs)
+            ac = BytesAhoCorasick(pats, kind)
+            m, moffs, gtotal = gpu_batch(ac, body, offs)
+            assert gtotal == total and np.array_equal(m, rec)
+
+
+def test_implementations_agree(kernel):
+    hay = "hello, world, hello again ☃ héllo"
+    pats = ["hello", "world", "☃ h", "llo"]
+    res = [AhoCorasick(pats, implementation=i).find_matches_as_indexes(hay, overlapping=True)
+           for i in (None, Implementation.NoncontiguousNFA, Implementation.ContiguousNFA, Implementation.DFA)]
+    assert all(r == res[0] for r in res) and len(res[0]) >= 4
+
+
+def test_output_capacity_retry():
+    pats = [b"a"]
+    data = np.full(50_000, 97, dtype=np.uint8)
+    offs = np.array([0, 50_000], dtype=np.int64)
+    ac = BytesAhoCorasick(pats)
+    m, moffs, total = ac.scan_device(dev(data), dev(offs), capacity=1024)
+    assert total == 50_000 and moffs.tolist() == [0, 50_000]
+    got = m.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got[:, 2], np.arange(50_000)) and np.array_equal(got[:, 3], np.arange(1, 50_001))
+
+
+# ---------------------------------------------------------------- full-size properties (no oracle at this size)
+def test_full_size_properties_config2():
+    """BASELINE config 2 at full size: sharding invariance (scan of the batch ==
+    concatenation of scans of its halves), every hit slices back to its pattern,
+    and the known structure of the workload (only i % 90 == 0 haystacks carry names)."""
+    pats, data, offs = W.config2(20_000)
+    ac = AhoCorasick(pats, implementation=Implementation.DFA)
+    d, o = dev(data), dev(offs)
+    m, moffs, total = ac.scan_device(d, o)
+    m = m.cpu().numpy().view(np.uint32).copy()
+    moffs = moffs.cpu().numpy().copy()
+    half = 10_000
+    m1, o1, t1 = ac.scan_device(d[: offs[half]], o[: half + 1])
+    m1 = m1.cpu().numpy().view(np.uint32).copy()
+    m2, o2, t2 = ac.scan_device(d[offs[half]:], dev(offs[half:] - offs[half]))
+    m2 = m2.cpu().numpy().view(np.uint32).copy()
+    m2[:, 0] += half
+    assert t1 + t2 == total and np.array_equal(np.concatenate([m1, m2]), m)
+    # plain kernel agrees with the staged kernel
+    set_kernel(1)
+    try:
+        mp, _, tp = ac.scan_device(d, o)
+        assert tp == total and np.array_equal(mp.cpu().numpy().view(np.uint32), m)
+    finally:
+        set_kernel(0)
+    hays_with = np.unique(m[:, 0])
+    assert len(hays_with) > 0 and np.all(hays_with % 90 == 0)
+    for h, pid, s, e in m[:200]:
+        text = data[offs[h]:offs[h + 1]].tobytes().decode("utf-8")
+        assert text[s:e] == pats[pid]

@@ -1,0 +1,81 @@
+"""CPU tests of the multi-GPU host logic with world_size-2 gloo: partition ->
+per-shard scan -> gather == unsharded result.  The per-shard scan is stood in
+for by the oracle here (no GPU in this container); on GPUs bench.py --gpus N
+drives the same gather over NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from ahocorasick_rs_b200 import workloads as W
+from ahocorasick_rs_b200.sharding import gather_match_lists, partition_by_bytes, scan_sharded
+
+
+def test_partition_by_bytes_covers_everything():
+    rng = np.random.default_rng(0)
+    for world in (1, 2, 3, 8):
+        lens = rng.integers(0, 1000, size=257)
+        offs = np.zeros(258, dtype=np.int64)
+        np.cumsum(lens, out=offs[1:])
+        offs += 13
+        parts = partition_by_bytes(offs, world)
+        assert parts[0][0] == 0 and parts[-1][1] == 257
+        assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+        sizes = [offs[hi] - offs[lo] for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 2000
+    assert partition_by_bytes(np.array([0, 0, 0], dtype=np.int64), 4)[-1][1] == 2
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import Oracle
+    pats = [b"ab", b"abc", b"ca", b"b"]
+    data, offs = W.ragged(500, 200, b"abc", seed=3)
+    orc = Oracle(pats, "Standard")
+
+    def scan_fn(d, o):
+        _, _, rec = orc.scan_batch(d, o)
+        return torch.from_numpy(rec.astype(np.int64).astype(np.int32).reshape(-1, 4))
+
+    full = scan_sharded(scan_fn, data, offs)
+    _, _, exp = orc.scan_batch(data, offs)
+    ok = np.array_equal(full.numpy().astype(np.uint32), exp)
+    # gather to one destination only
+    lo, hi = partition_by_bytes(offs, world)[rank]
+    local = scan_fn(data[offs[lo]:offs[hi]], offs[lo:hi + 1] - offs[lo])
+    only0 = gather_match_lists(local, lo, dst=0)
+    ok = ok and ((only0 is None) == (rank != 0))
+    if rank == 0:
+        ok = ok and np.array_equal(only0.numpy().astype(np.uint32), exp)
+    q.put((rank, bool(ok), int(full.shape[0])))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_scan_and_gather_equals_unsharded():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(ok for _, ok, _ in res), res
+    assert res[0][2] == res[1][2] > 100
