@@ -59,10 +59,17 @@ def lib():
         L.acb_scratch_words.argtypes = [C.c_uint64]
         L.acb_chunk_count.restype = C.c_uint64
         L.acb_chunk_count.argtypes = [C.c_uint64, C.c_uint32]
-        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int,
-                                     C.POINTER(Workspace), C.c_void_p]
-        L.acb_scan_chunked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int,
-                                       C.POINTER(Workspace), C.c_void_p]
+        L.acb_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int,
+                                  C.c_void_p, C.c_void_p]
+        L.acb_hot_bytes.restype = C.c_uint64
+        L.acb_hot_bytes.argtypes = [C.c_void_p, C.c_uint32]
+        L.acb_hot_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.acb_hot_rows.restype = C.c_uint32
+        L.acb_hot_rows.argtypes = [C.c_void_p]
+        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64,
+                                     C.c_int, C.c_int, C.POINTER(Workspace), C.c_void_p]
+        L.acb_scan_chunked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                       C.c_uint32, C.c_int, C.POINTER(Workspace), C.c_void_p]
         _lib = L
     return _lib
 
@@ -76,4 +83,5 @@ EXPORTS = [
     "acb_num_columns", "acb_max_pattern_len", "acb_min_pattern_len", "acb_match_kind", "acb_image_bytes",
     "acb_image_write", "acb_scratch_words", "acb_scan_batch", "acb_chunk_count", "acb_scan_chunked",
     "acb_launch_count", "acb_set_tuning", "acb_timing_enable", "acb_timing_read",
+    "acb_profile", "acb_hot_bytes", "acb_hot_build", "acb_hot_rows",
 ]

@@ -290,4 +290,82 @@ Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_
     return A;
 }
 
+static uint32_t hot_rows_for(const Automaton &a, uint32_t max_rows) {
+    uint32_t H = max_rows;
+    if (H > a.hdr.n_states - 1) H = a.hdr.n_states - 1;  // kDead is never hot
+    if (H > 65534) H = 65534;
+    if (H < 1) H = 1;
+    return H;
+}
+
+uint64_t hot_image_bytes(const Automaton &a, uint32_t max_rows) {
+    const uint32_t H = hot_rows_for(a, max_rows);
+    uint64_t off = align16(sizeof(HotHeader));
+    off = align16(off + uint64_t(H + 1) * a.hdr.n_cols * 2);
+    off = align16(off + uint64_t(H + 1) * 4);
+    off = align16(off + uint64_t(a.hdr.n_states) * 2);
+    return off;
+}
+
+void build_hot_image(const Automaton &a, const uint32_t *visits, uint32_t max_rows, uint8_t *dst) {
+    const ImageHeader &ih = a.hdr;
+    const uint32_t H = hot_rows_for(a, max_rows);
+    const uint32_t n_cols = ih.n_cols, n_states = ih.n_states;
+    HotHeader hh{};
+    hh.magic = kHotMagic;
+    hh.n_rows = H;
+    hh.n_cols = n_cols;
+    hh.n_states = n_states;
+    uint64_t off = align16(sizeof(HotHeader));
+    hh.off_table = off;
+    off = align16(off + uint64_t(H + 1) * n_cols * 2);
+    hh.off_hot2full = off;
+    off = align16(off + uint64_t(H + 1) * 4);
+    hh.off_full2hot = off;
+    off = align16(off + uint64_t(n_states) * 2);
+    hh.total_bytes = off;
+    std::memset(dst, 0, off);
+    std::memcpy(dst, &hh, sizeof(hh));
+    uint16_t *table = reinterpret_cast<uint16_t *>(dst + hh.off_table);
+    uint32_t *hot2full = reinterpret_cast<uint32_t *>(dst + hh.off_hot2full);
+    uint16_t *full2hot = reinterpret_cast<uint16_t *>(dst + hh.off_full2hot);
+    for (uint32_t s = 0; s < n_states; s++) full2hot[s] = kNotHot;
+
+    // choose the rows: root, then sampled states by visit count, then shallow states
+    uint32_t n = 0;
+    auto take = [&](uint32_t s) {
+        if (n < H && s != kDead && full2hot[s] == kNotHot) {
+            full2hot[s] = static_cast<uint16_t>(n);
+            hot2full[n++] = s;
+        }
+    };
+    take(kRoot);
+    if (visits) {
+        std::vector<uint32_t> seen;
+        for (uint32_t s = kRoot; s < n_states; s++)
+            if (visits[s]) seen.push_back(s);
+        const size_t keep = std::min<size_t>(seen.size(), H);
+        std::partial_sort(seen.begin(), seen.begin() + keep, seen.end(), [&](uint32_t x, uint32_t y) {
+            return visits[x] != visits[y] ? visits[x] > visits[y] : x < y;
+        });
+        for (size_t i = 0; i < keep; i++) take(seen[i]);
+    }
+    for (uint32_t s = kRoot; s < n_states && n < H; s++) take(s);
+    // n == H here because H <= n_states - 1
+
+    const uint32_t *T = reinterpret_cast<const uint32_t *>(a.image.data() + ih.off_trans);
+    for (uint32_t h = 0; h < H; h++) {
+        const uint32_t *row = T + uint64_t(hot2full[h]) * n_cols;
+        uint16_t *out = table + uint64_t(h) * n_cols;
+        for (uint32_t c = 0; c < n_cols; c++) {
+            const uint32_t e = row[c], t = e & kStateMask;
+            uint16_t v = static_cast<uint16_t>(H);
+            if (!(e & kMatchFlag) && t != kDead && full2hot[t] != kNotHot) v = full2hot[t];
+            out[c] = v;
+        }
+    }
+    for (uint32_t c = 0; c < n_cols; c++) table[uint64_t(H) * n_cols + c] = static_cast<uint16_t>(H);
+    hot2full[H] = kDead;
+}
+
 }  // namespace acb

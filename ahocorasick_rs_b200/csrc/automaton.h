@@ -46,6 +46,23 @@ struct ImageHeader {
 
 constexpr uint32_t kImageMagic = 0x30424341u;  // "ACB0"
 
+// The hot image: the part of the automaton the staged kernel keeps in shared
+// memory.  Rows are ordered hottest first (by sampled visit counts, the root
+// always first, then shallow states as filler), so a kernel that can only fit
+// H' < n_rows rows takes a prefix.  Entries are HOT INDICES; n_rows = trap.
+struct HotHeader {
+    uint32_t magic;
+    uint32_t n_rows;    // H
+    uint32_t n_cols;
+    uint32_t n_states;
+    uint64_t off_table;     // u16[(H + 1) * n_cols]; row H is all H
+    uint64_t off_hot2full;  // u32[H + 1]
+    uint64_t off_full2hot;  // u16[n_states]; 0xffff = not hot
+    uint64_t total_bytes;
+};
+constexpr uint32_t kHotMagic = 0x31424341u;  // "ACB1"
+constexpr uint16_t kNotHot = 0xffffu;
+
 struct Automaton {
     ImageHeader hdr{};
     std::vector<uint8_t> image;  // header + tables, ready to copy to the device
@@ -55,5 +72,10 @@ struct Automaton {
 // Builds the automaton; throws std::runtime_error with a message on failure.
 Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_t n, int match_kind,
                            int implementation);
+
+// Size of / builder for the hot image with at most max_rows rows.  visits may be
+// null (no profile yet: breadth-first prefix) or n_states sampled visit counts.
+uint64_t hot_image_bytes(const Automaton &a, uint32_t max_rows);
+void build_hot_image(const Automaton &a, const uint32_t *visits, uint32_t max_rows, uint8_t *dst);
 
 }  // namespace acb

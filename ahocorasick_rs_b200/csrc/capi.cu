@@ -18,8 +18,38 @@ __global__ void __launch_bounds__(128) scan_plain_kernel(DevImage im, Units U, S
     for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U.n_units; u += (int64_t)gridDim.x * blockDim.x) {
         UnitCtx c;
         init_unit<CP>(c, U, u);
-        exact_scan<MODE, CP>(c, im, out, false, 0, 0, 0);
+        exact_scan<MODE, CP>(c, im, out, false, 0, 0, HotMap{nullptr, 0});
         out.unit_counts[u] = c.nemit;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// profile kernel: walks a sample of the input through the dense table and
+// counts state visits; the host ranks states by these counts to choose the rows
+// the staged kernel keeps in shared memory (automaton.cpp: build_hot_image)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+profile_kernel(DevImage im, Units U, uint32_t *visits, int64_t n_samples, uint32_t max_bytes, int restart_on_match) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_samples) return;
+    const uint8_t *p;
+    uint64_t len;
+    if (U.chunk == 0) {
+        const int64_t u = (U.n_units * i) / n_samples;
+        p = U.bytes + U.offsets[u];
+        len = (uint64_t)(U.offsets[u + 1] - U.offsets[u]);
+    } else {
+        const uint64_t lo = (U.len / (uint64_t)n_samples) * (uint64_t)i;
+        p = U.bytes + lo;
+        len = U.len - lo;
+    }
+    if (len > max_bytes) len = max_bytes;
+    uint32_t s = kRoot;
+    for (uint64_t k = 0; k < len; k++) {
+        const uint32_t e = __ldg(im.trans + (size_t)s * im.n_cols + __ldg(im.colmap + __ldg(p + k)));
+        s = e & kStateMask;
+        if (s == kDead || (restart_on_match && (e & kMatchFlag))) s = kRoot;
+        atomicAdd(visits + s, 1u);
     }
 }
 
@@ -233,6 +263,20 @@ int acb_image_write(const acb_automaton *a, void *host_dst, uint64_t dst_bytes) 
     return ACB_OK;
 }
 
+uint64_t acb_hot_bytes(const acb_automaton *a, uint32_t max_rows) { return hot_image_bytes(*a->impl, max_rows); }
+
+int acb_hot_build(const acb_automaton *a, const uint32_t *host_visits, uint32_t max_rows, void *host_dst, uint64_t dst_bytes) {
+    if (!a || !host_dst) return fail(ACB_EINVAL, "null argument");
+    if (dst_bytes < hot_image_bytes(*a->impl, max_rows)) return fail(ACB_ECAPACITY, "hot image buffer too small");
+    build_hot_image(*a->impl, host_visits, max_rows, static_cast<uint8_t *>(host_dst));
+    return ACB_OK;
+}
+
+uint32_t acb_hot_rows(const void *host_hot) {
+    const HotHeader *h = static_cast<const HotHeader *>(host_hot);
+    return (h && h->magic == kHotMagic) ? h->n_rows : 0;
+}
+
 uint64_t acb_scratch_words(uint64_t n_units) {
     const uint64_t tiles = (n_units + kScanTile - 1) / kScanTile;
     // [0] task counter | tile sums | chunk code point counts (u32, n_units) | chunk code point offsets (n_units + 1)
@@ -296,8 +340,8 @@ int launch_plain(const DevImage &im, const Units &U, const Sink &out, const Devi
 }
 
 template <int MODE, bool CP, int COLMODE>
-int launch_staged(const DevImage &im, const Units &U, const Sink &out, const DeviceInfo &d, unsigned int *task_counter,
-                  cudaStream_t st) {
+int launch_staged(const DevImage &im, const DevHot &hot, const Units &U, const Sink &out, const DeviceInfo &d,
+                  unsigned int *task_counter, cudaStream_t st) {
     auto kern = scan_staged_kernel<MODE, CP, COLMODE>;
     const int64_t tasks = (U.n_units + 31) / 32;
     const int ctas = d.sms;
@@ -310,33 +354,49 @@ int launch_staged(const DevImage &im, const Units &U, const Sink &out, const Dev
     if (budget < stage_bytes + 256 + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
     uint32_t rows = (budget - stage_bytes - 256 - 128) / row_bytes;  // includes the trap row
     uint32_t H = rows - 1;
-    if (H > im.n_states) H = im.n_states;
-    if (H > 65535) H = 65535;
-    if (g_tuning.hot_rows > 1 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
-    if (H < 2) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
+    if (H > hot.n_rows) H = hot.n_rows;
+    if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
+    if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
     const uint32_t hot_bytes = (((H + 1) * row_bytes) + 127u) & ~127u;
     const uint32_t smem = hot_bytes + 256 + stage_bytes;
     static thread_local int configured_for = -1;
     (void)configured_for;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     CUDA_OK(cudaMemsetAsync(task_counter, 0, sizeof(unsigned int), st));
-    kern<<<ctas, warps * 32, smem, st>>>(im, U, out, H, hot_bytes, task_counter);
+    kern<<<ctas, warps * 32, smem, st>>>(im, hot, U, out, H, hot_bytes, task_counter, out.total + 2);
     g_launches++;
     return ACB_OK;
 }
 
 template <int MODE, bool CP>
-int launch_scan(const ImageHeader &h, const DevImage &im, const Units &U, const Sink &out, const DeviceInfo &d,
-                unsigned int *task_counter, cudaStream_t st) {
+int launch_scan(const ImageHeader &h, const DevImage &im, const DevHot *hot, const Units &U, const Sink &out,
+                const DeviceInfo &d, unsigned int *task_counter, cudaStream_t st) {
     int kernel = g_tuning.kernel;
     if (kernel == 0) kernel = 2;
-    if (kernel == 2 && im.n_cols * 2u * 3u + 4096u > (uint32_t)d.max_smem_optin) kernel = 1;
+    if (!hot) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
     if (kernel == 1) return launch_plain<MODE, CP>(im, U, out, d, st);
-    if (h.col_mode == kColRange) return launch_staged<MODE, CP, kColRange>(im, U, out, d, task_counter, st);
-    return launch_staged<MODE, CP, kColClass>(im, U, out, d, task_counter, st);
+    if (h.col_mode == kColRange) return launch_staged<MODE, CP, kColRange>(im, *hot, U, out, d, task_counter, st);
+    return launch_staged<MODE, CP, kColClass>(im, *hot, U, out, d, task_counter, st);
 }
 
-int run_scan(const acb_automaton *a, const void *dev_image, const Units &U, int mode, int codepoints,
+// dev_hot points at a device copy of a hot image; hot_rows is its row count (the
+// host knows it: acb_hot_rows on the host copy), because the header lives on the device
+int make_hot_view(const acb_automaton *a, const void *dev_hot, uint32_t hot_rows, DevHot &v) {
+    const ImageHeader &ih = a->impl->hdr;
+    if (hot_rows < 1 || hot_rows > 65534) return fail(ACB_EINVAL, "bad hot image row count");
+    auto align16 = [](uint64_t x) { return (x + 15) & ~uint64_t(15); };
+    const uint8_t *b = static_cast<const uint8_t *>(dev_hot);
+    uint64_t off = align16(sizeof(HotHeader));
+    v.table = reinterpret_cast<const uint16_t *>(b + off);
+    off = align16(off + uint64_t(hot_rows + 1) * ih.n_cols * 2);
+    v.hot2full = reinterpret_cast<const uint32_t *>(b + off);
+    off = align16(off + uint64_t(hot_rows + 1) * 4);
+    v.full2hot = reinterpret_cast<const uint16_t *>(b + off);
+    v.n_rows = hot_rows;
+    return ACB_OK;
+}
+
+int run_scan(const acb_automaton *a, const void *dev_image, const DevHot *hot, const Units &U, int mode, int codepoints,
              const acb_workspace *ws, cudaStream_t st) {
     DeviceInfo d;
     int rc = device_info(d);
@@ -353,7 +413,7 @@ int run_scan(const acb_automaton *a, const void *dev_image, const Units &U, int 
     unsigned int *task_counter = reinterpret_cast<unsigned int *>(ws->dev_scratch);
     unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
 
-    CUDA_OK(cudaMemsetAsync(ws->dev_total, 0, 2 * sizeof(uint64_t), st));
+    CUDA_OK(cudaMemsetAsync(ws->dev_total, 0, 4 * sizeof(uint64_t), st));
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (g_timing && U.n_units > 0) {
         CUDA_OK(cudaEventCreate(&ev0));
@@ -363,14 +423,14 @@ int run_scan(const acb_automaton *a, const void *dev_image, const Units &U, int 
         const bool cp = codepoints != 0;
         if (ev0) CUDA_OK(cudaEventRecord(ev0, st));
         if (mode == kModeStandard)
-            rc = cp ? launch_scan<kModeStandard, true>(h, im, U, out, d, task_counter, st)
-                    : launch_scan<kModeStandard, false>(h, im, U, out, d, task_counter, st);
+            rc = cp ? launch_scan<kModeStandard, true>(h, im, hot, U, out, d, task_counter, st)
+                    : launch_scan<kModeStandard, false>(h, im, hot, U, out, d, task_counter, st);
         else if (mode == kModeLeftmost)
-            rc = cp ? launch_scan<kModeLeftmost, true>(h, im, U, out, d, task_counter, st)
-                    : launch_scan<kModeLeftmost, false>(h, im, U, out, d, task_counter, st);
+            rc = cp ? launch_scan<kModeLeftmost, true>(h, im, hot, U, out, d, task_counter, st)
+                    : launch_scan<kModeLeftmost, false>(h, im, hot, U, out, d, task_counter, st);
         else
-            rc = cp ? launch_scan<kModeOverlap, true>(h, im, U, out, d, task_counter, st)
-                    : launch_scan<kModeOverlap, false>(h, im, U, out, d, task_counter, st);
+            rc = cp ? launch_scan<kModeOverlap, true>(h, im, hot, U, out, d, task_counter, st)
+                    : launch_scan<kModeOverlap, false>(h, im, hot, U, out, d, task_counter, st);
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());
         if (ev1) {
@@ -410,8 +470,37 @@ int check_ws(const acb_workspace *ws) {
 
 extern "C" {
 
-int acb_scan_batch(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, const int64_t *dev_offsets,
-                   int64_t n_haystacks, int overlapping, int codepoints, const acb_workspace *ws, void *stream) {
+int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, const int64_t *dev_offsets,
+                int64_t n_haystacks, uint64_t len, int overlapping, uint32_t *dev_visits, void *stream) {
+    if (!a || !dev_image || !dev_visits) return fail(ACB_EINVAL, "bad argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const ImageHeader &h = a->impl->hdr;
+    CUDA_OK(cudaMemsetAsync(dev_visits, 0, uint64_t(h.n_states) * 4, st));
+    Units U{};
+    U.bytes = dev_bytes;
+    U.offsets = dev_offsets;
+    U.n_units = n_haystacks;
+    U.len = len;
+    U.chunk = dev_offsets ? 0 : 1;
+    int64_t n_samples = 256;
+    if (dev_offsets) {
+        if (n_haystacks < 1) return ACB_OK;
+        if (n_samples > n_haystacks) n_samples = n_haystacks;
+    } else {
+        if (len == 0) return ACB_OK;
+        if ((uint64_t)n_samples > len / 1024 + 1) n_samples = (int64_t)(len / 1024 + 1);
+    }
+    const DevImage im = make_view(h, dev_image);
+    const int restart = (!overlapping && h.match_kind == ACB_STANDARD) ? 1 : 0;
+    profile_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, st>>>(im, U, dev_visits, n_samples, 1024, restart);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
+                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, int overlapping,
+                   int codepoints, const acb_workspace *ws, void *stream) {
     if (!a || !dev_image || !dev_offsets || n_haystacks < 0) return fail(ACB_EINVAL, "bad argument");
     if (n_haystacks > 0xffffffffll) return fail(ACB_EINVAL, "too many haystacks in one batch");
     const int kind = (int)a->impl->hdr.match_kind;
@@ -426,11 +515,14 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const uint8_t 
     U.n_units = n_haystacks;
     U.chunk = 0;
     const int mode = overlapping ? kModeOverlap : (kind == ACB_STANDARD ? kModeStandard : kModeLeftmost);
-    return run_scan(a, dev_image, U, mode, codepoints, ws, static_cast<cudaStream_t>(stream));
+    DevHot hot;
+    if (dev_hot && (rc = make_hot_view(a, dev_hot, hot_rows, hot))) return rc;
+    return run_scan(a, dev_image, dev_hot ? &hot : nullptr, U, mode, codepoints, ws, static_cast<cudaStream_t>(stream));
 }
 
-int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, uint64_t len,
-                     uint32_t chunk_bytes, int codepoints, const acb_workspace *ws, void *stream) {
+int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
+                     const uint8_t *dev_bytes, uint64_t len, uint32_t chunk_bytes, int codepoints,
+                     const acb_workspace *ws, void *stream) {
     if (!a || !dev_image || (!dev_bytes && len)) return fail(ACB_EINVAL, "bad argument");
     if (chunk_bytes < 64) return fail(ACB_EINVAL, "chunk_bytes must be at least 64");
     if (len >= 0xffffffffull) return fail(ACB_EINVAL, "haystacks of 4 GiB and more are not supported yet");
@@ -466,7 +558,9 @@ int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const uint8_
         CUDA_OK(cudaGetLastError());
         U.chunk_cp = reinterpret_cast<const uint64_t *>(offs);
     }
-    return run_scan(a, dev_image, U, kModeOverlap, codepoints, ws, st);
+    DevHot hot;
+    if (dev_hot && (rc = make_hot_view(a, dev_hot, hot_rows, hot))) return rc;
+    return run_scan(a, dev_image, dev_hot ? &hot : nullptr, U, kModeOverlap, codepoints, ws, st);
 }
 
 }  // extern "C"

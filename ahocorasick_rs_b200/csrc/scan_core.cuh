@@ -102,13 +102,19 @@ __device__ __forceinline__ void report(UnitCtx &c, const DevImage &im, const Sin
     c.nemit++;
 }
 
+// Where the staged fast path may resume: full2hot[state] < hot_limit.
+struct HotMap {
+    const uint16_t *full2hot;
+    uint32_t hot_limit;
+};
+
 // Runs the exact scanner from c.at.  It returns when the unit is finished
 // (c.at == c.end with nothing pending), or -- if stop_hot is set -- as soon as
-//   at >= min_at, (at - phase) % 16 == 0, state < hot_limit and nothing pending,
+//   at >= min_at, (at - phase) % 16 == 0, the state is hot and nothing is pending,
 // i.e. at a point where the staged fast path may take over again.
 template <int MODE, bool CP>
 __device__ __noinline__ void exact_scan(UnitCtx &c, const DevImage &im, const Sink &out, bool stop_hot,
-                                        uint32_t min_at, uint32_t phase, uint32_t hot_limit) {
+                                        uint32_t min_at, uint32_t phase, HotMap hm) {
     uint32_t s = c.state, at = c.at;
     const uint32_t end = c.end;
     for (;;) {
@@ -128,8 +134,8 @@ __device__ __noinline__ void exact_scan(UnitCtx &c, const DevImage &im, const Si
         } else {
             if (at == end) break;
         }
-        if (stop_hot && at >= min_at && ((at - phase) & 15u) == 0 && s < hot_limit && s != kDead &&
-            (MODE != kModeLeftmost || !c.have))
+        if (stop_hot && at >= min_at && ((at - phase) & 15u) == 0 && (MODE != kModeLeftmost || !c.have) &&
+            (uint32_t)__ldg(hm.full2hot + s) < hm.hot_limit)
             break;
         const uint32_t col = __ldg(im.colmap + ld_u8(c.base + at));
         const uint32_t e = __ldg(im.trans + (size_t)s * im.n_cols + col);

@@ -2,9 +2,10 @@
 // shared memory, haystack bytes staged through shared memory with cp.async.
 //
 // Layout per CTA (dynamic shared memory):
-//   [ hot table : (H + 1) rows x n_cols u16 ]  rows 0..H-1 are the H shallowest
-//        states (ids are breadth-first, so "shallow" = "low id"); row H is the
-//        TRAP row.  An entry is the next state if that state is < H and is
+//   [ hot table : (H + 1) rows x n_cols u16 ]  rows 0..H-1 are the H hottest
+//        states of the hot image (automaton.h: HotHeader; ranked by sampled
+//        visit counts), entries are hot indices; row H is the TRAP row.  An
+//        entry is the next state's hot index if that state is hot and is
 //        neither a match state nor the dead state, else H.  The trap row maps
 //        everything to H, so a lane that left the hot set stays at H and ONE
 //        compare per 16 bytes detects it; the 16 bytes are then redone by
@@ -67,30 +68,36 @@ __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, u
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Views into the hot image (global memory).
+struct DevHot {
+    const uint16_t *table;
+    const uint32_t *hot2full;
+    const uint16_t *full2hot;
+    uint32_t n_rows;
+};
+
 template <int MODE, bool CP, int COLMODE>
 __global__ void __launch_bounds__(1024, 1)
-scan_staged_kernel(DevImage im, Units U, Sink out, uint32_t H, uint32_t hot_bytes, unsigned int *task_counter) {
+scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, uint32_t hot_bytes,
+                   unsigned int *task_counter, unsigned long long *trap_stats) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint16_t *hot = reinterpret_cast<uint16_t *>(smem);
     uint8_t *cmap = smem + hot_bytes;                       // 256 B
     uint8_t *stage_all = smem + hot_bytes + 256;            // 128-aligned by construction
 
-    // ---- prologue: derive the hot table from the dense table (L2 resident) ----
+    // ---- prologue: the first H rows of the hot image (L2 resident), clamped to this
+    // kernel's H (H <= hot_img.n_rows: rows are hottest-first, so a prefix is valid) ----
     {
-        const uint32_t n = (H + 1) * im.n_cols;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
-            const uint32_t s = i / im.n_cols;
-            uint32_t v = H;
-            if (s != kDead && s < H) {
-                const uint32_t e = __ldg(im.trans + i);
-                const uint32_t t = e & kStateMask;
-                if (!(e & kMatchFlag) && t != kDead && t < H) v = t;
-            }
-            hot[i] = (uint16_t)v;
-        }
+        const uint32_t n = H * im.n_cols;
+        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) hot[i] = (uint16_t)min((uint32_t)__ldg(hot_img.table + i), H);
+        for (uint32_t i = threadIdx.x; i < im.n_cols; i += blockDim.x) hot[n + i] = (uint16_t)H;
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
     }
     __syncthreads();
+    HotMap hm;
+    hm.full2hot = hot_img.full2hot;
+    hm.hot_limit = H;
+    uint32_t n_groups = 0, n_traps = 0;
 
     FastTab ft;
     ft.hot = hot;
@@ -127,9 +134,9 @@ scan_staged_kernel(DevImage im, Units U, Sink out, uint32_t H, uint32_t hot_byte
             nchunks = (pe > a0) ? (uint32_t)((pe - a0 + kChunk - 1) / kChunk) : 0;
             rel0 = (int64_t)c.at - (int64_t)(p0 - a0);
             // head: bytes before the first 16-byte boundary
-            exact_scan<MODE, CP>(c, im, out, true, c.at, phase, H);
+            exact_scan<MODE, CP>(c, im, out, true, c.at, phase, hm);
             pos = c.at;
-            s = c.state;
+            s = __ldg(hot_img.full2hot + c.state);  // a hot index unless the unit is already finished
             if (CP) cp_catch_up(c, pos);
         }
         uint32_t kmax = nchunks;
@@ -172,6 +179,7 @@ scan_staged_kernel(DevImage im, Units U, Sink out, uint32_t H, uint32_t hot_byte
                     t = fstep4<COLMODE>(t, w.y, ft);
                     t = fstep4<COLMODE>(t, w.z, ft);
                     t = fstep4<COLMODE>(t, w.w, ft);
+                    n_groups++;
                     if (t != H) {
                         s = t;
                         if (CP) {
@@ -188,10 +196,11 @@ scan_staged_kernel(DevImage im, Units U, Sink out, uint32_t H, uint32_t hot_byte
                         pos += 16;
                     } else {
                         // something happened in these 16 bytes: redo them exactly
-                        c.state = s;
+                        n_traps++;
+                        c.state = __ldg(hot_img.hot2full + s);
                         c.at = pos;
-                        exact_scan<MODE, CP>(c, im, out, true, pos + 16, phase, H);
-                        s = c.state;
+                        exact_scan<MODE, CP>(c, im, out, true, pos + 16, phase, hm);
+                        s = __ldg(hot_img.full2hot + c.state);
                         pos = c.at;
                         if (CP) cp_catch_up(c, pos);
                     }
@@ -200,11 +209,23 @@ scan_staged_kernel(DevImage im, Units U, Sink out, uint32_t H, uint32_t hot_byte
         }
         if (valid) {
             // tail: whatever is left after the last full 16-byte group
-            c.state = s;
-            c.at = pos;
-            exact_scan<MODE, CP>(c, im, out, false, 0, 0, 0);
+            if (pos < c.end) {
+                c.state = __ldg(hot_img.hot2full + s);
+                c.at = pos;
+                exact_scan<MODE, CP>(c, im, out, false, 0, 0, hm);
+            }
             out.unit_counts[c.unit] = c.nemit;
         }
+    }
+    // how well the hot set fits the data: the host re-profiles when traps are frequent
+#pragma unroll
+    for (int d = 16; d; d >>= 1) {
+        n_groups += __shfl_xor_sync(0xffffffffu, n_groups, d);
+        n_traps += __shfl_xor_sync(0xffffffffu, n_traps, d);
+    }
+    if (lane == 0) {
+        atomicAdd(trap_stats, (unsigned long long)n_groups);
+        atomicAdd(trap_stats + 1, (unsigned long long)n_traps);
     }
 }
 

@@ -77,6 +77,7 @@ class _Automaton:
         self.num_columns = int(L.acb_num_columns(h))
         self.max_pattern_len = int(L.acb_max_pattern_len(h))
         self._images = {}      # device index -> uint8 tensor
+        self._hot = {}         # device index -> dict(tensor, rows, reprofile, calls, backoff)
         self._ws = {}          # device index -> dict of tensors
         self._lock = threading.Lock()
 
@@ -102,6 +103,60 @@ class _Automaton:
             self._images[idx] = img
         return img
 
+    # ---- the hot image (rows kept in shared memory), chosen from a sample of the data ----
+    HOT_TABLE_BYTES = 96 * 1024
+
+    def _max_hot_rows(self):
+        return max(2, min(4096, self.HOT_TABLE_BYTES // (2 * self.num_columns) - 1))
+
+    def _upload_hot(self, idx, visits_host):
+        torch = _torch()
+        rows = self._max_hot_rows()
+        nbytes = int(self._L.acb_hot_bytes(self._h, rows))
+        host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+        vp = visits_host.ctypes.data if visits_host is not None else None
+        rc = self._L.acb_hot_build(self._h, vp, rows, host.data_ptr(), nbytes)
+        if rc != _capi.ACB_OK:
+            raise RuntimeError(_capi.last_error())
+        n_rows = int(self._L.acb_hot_rows(host.data_ptr()))
+        return host.to(torch.device("cuda", idx)), n_rows
+
+    def hot(self, device, data=None, offsets=None, overlapping=False):
+        """The hot image on `device`.  Built from a profile of (data, offsets) the
+        first time this automaton scans on the device, and again -- with
+        exponential back-off -- when the kernel reports that the fast path keeps
+        falling out of the hot set (the data changed character)."""
+        torch = _torch()
+        idx = device.index
+        st = self._hot.get(idx)
+        need = st is None or st["reprofile"]
+        if need and data is not None and data.numel() > 0:
+            img = self.image(device)
+            visits = torch.empty(self.num_states, dtype=torch.int32, device=device)
+            stream = torch.cuda.current_stream(device).cuda_stream
+            n = 0 if offsets is None else offsets.numel() - 1
+            rc = self._L.acb_profile(self._h, img.data_ptr(), data.data_ptr(),
+                                     None if offsets is None else offsets.data_ptr(), n, data.numel(),
+                                     int(bool(overlapping)), visits.data_ptr(), stream)
+            if rc != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            vh = visits.cpu().numpy().view(np.uint32)
+            t, rows = self._upload_hot(idx, vh)
+            backoff = (st["backoff"] * 2) if st else 1
+            st = {"tensor": t, "rows": rows, "reprofile": False, "calls": 0, "backoff": backoff}
+            self._hot[idx] = st
+        elif st is None:
+            t, rows = self._upload_hot(idx, None)
+            st = {"tensor": t, "rows": rows, "reprofile": True, "calls": 0, "backoff": 1}
+            self._hot[idx] = st
+        return st
+
+    def _note_trap_stats(self, st, groups: int, traps: int):
+        st["calls"] += 1
+        if groups > 4096 and traps * 10 > groups and st["calls"] >= st["backoff"]:
+            st["reprofile"] = True
+            st["calls"] = 0
+
     def _workspace(self, device, n_units: int, capacity: int):
         torch = _torch()
         idx = device.index
@@ -118,7 +173,7 @@ class _Automaton:
                 "unit_counts": torch.empty(n_alloc, dtype=torch.int32, device=dev),
                 "unit_offsets": torch.empty(n_alloc + 1, dtype=torch.int64, device=dev),
                 "scratch": torch.empty(int(self._L.acb_scratch_words(n_alloc)), dtype=torch.int64, device=dev),
-                "total": torch.zeros(2, dtype=torch.int64, device=dev),
+                "total": torch.zeros(4, dtype=torch.int64, device=dev),
                 "out": torch.empty((cap, 4), dtype=torch.int32, device=dev),
             }
             self._ws[idx] = ws
@@ -160,17 +215,21 @@ class _Automaton:
         cap = capacity or max(1024, n * 2)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with self._lock, torch.cuda.device(dev):
+            hot = self.hot(dev, data, offsets, overlapping)
             while True:
                 ws = self._workspace(dev, n, cap)
                 st = self._ws_struct(ws)
-                rc = self._L.acb_scan_batch(self._h, img.data_ptr(), data.data_ptr(), offsets.data_ptr(), n,
+                rc = self._L.acb_scan_batch(self._h, img.data_ptr(), hot["tensor"].data_ptr(), hot["rows"],
+                                            data.data_ptr(), offsets.data_ptr(), n,
                                             int(bool(overlapping)), int(bool(codepoints)), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
                     err = _capi.last_error()
                     raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
                 if not sync:
                     return ws["out"], ws["unit_offsets"][: n + 1], ws["total"]
-                total = int(ws["total"][0].item())
+                tot = ws["total"].tolist()
+                total = tot[0]
+                self._note_trap_stats(hot, tot[2], tot[3])
                 if total <= ws["capacity"]:
                     return ws["out"][:total], ws["unit_offsets"][: n + 1], total
                 cap = total + total // 8 + 16
@@ -186,15 +245,19 @@ class _Automaton:
         cap = max(1024, n_units)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with self._lock, torch.cuda.device(dev):
+            hot = self.hot(dev, data, None, True)
             while True:
                 ws = self._workspace(dev, n_units, cap)
                 st = self._ws_struct(ws)
-                rc = self._L.acb_scan_chunked(self._h, img.data_ptr(), data.data_ptr(), data.numel(), chunk,
+                rc = self._L.acb_scan_chunked(self._h, img.data_ptr(), hot["tensor"].data_ptr(), hot["rows"],
+                                              data.data_ptr(), data.numel(), chunk,
                                               int(bool(codepoints)), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
                     err = _capi.last_error()
                     raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
-                total = int(ws["total"][0].item())
+                tot = ws["total"].tolist()
+                total = tot[0]
+                self._note_trap_stats(hot, tot[2], tot[3])
                 if total <= ws["capacity"]:
                     return ws["out"][:total], total
                 cap = total + total // 8 + 16

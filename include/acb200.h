@@ -95,6 +95,25 @@ uint64_t acb_image_bytes(const acb_automaton *a);
 int acb_image_write(const acb_automaton *a, void *host_dst, uint64_t dst_bytes);
 
 /*
+ * The hot image: the rows of the table the staged kernel keeps in shared memory,
+ * hottest first.  "Hot" is decided from data: acb_profile() walks a sample of a
+ * device-resident input through the automaton and counts state visits into
+ * dev_visits (u32[acb_num_states], zeroed by the call); the caller copies the
+ * counts to the host and hands them to acb_hot_build() (host_visits == NULL:
+ * no profile, shallowest states first), then uploads the result and passes it,
+ * with its row count, to the scans.  Which rows are hot changes speed only --
+ * everything the fast path cannot prove uneventful is redone by the exact
+ * scanner -- never results.  dev_hot == NULL selects the plain kernel.
+ * For acb_profile pass dev_offsets == NULL and len for one large haystack.
+ */
+int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, const int64_t *dev_offsets,
+                int64_t n_haystacks, uint64_t len, int overlapping, uint32_t *dev_visits, void *stream);
+uint64_t acb_hot_bytes(const acb_automaton *a, uint32_t max_rows);
+int acb_hot_build(const acb_automaton *a, const uint32_t *host_visits, uint32_t max_rows, void *host_dst,
+                  uint64_t dst_bytes);
+uint32_t acb_hot_rows(const void *host_hot);
+
+/*
  * Caller-provided device workspace for one scan.  n_units = number of scan
  * units: haystacks for acb_scan_batch, chunks for acb_scan_chunked
  * (acb_chunk_count()).
@@ -107,7 +126,8 @@ typedef struct acb_workspace {
     uint32_t *dev_unit_counts;  /* [n_units] matches per unit (output) */
     uint64_t *dev_unit_offsets; /* [n_units + 1] exclusive prefix sum of the counts (output) */
     uint64_t *dev_scratch;      /* [acb_scratch_words(n_units)] */
-    uint64_t *dev_total;        /* [2]: [0] = matches found, [1] = matches written to dev_out */
+    uint64_t *dev_total;        /* [4]: [0] = matches found, [1] = matches delivered in dev_out (0 = incomplete),
+                                   [2] = 16-byte groups the fast path tried, [3] = groups it had to hand to the exact scanner */
     acb_match *dev_out;         /* [out_capacity] final matches in the reference's order */
     uint64_t out_capacity;
 } acb_workspace;
@@ -133,9 +153,9 @@ uint64_t acb_scratch_words(uint64_t n_units);
  * overlapping on a non-Standard automaton returns ACB_EUNSUPPORTED before any
  * byte is read, like the reference.
  */
-int acb_scan_batch(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes,
-                   const int64_t *dev_offsets, int64_t n_haystacks, int overlapping, int codepoints,
-                   const acb_workspace *ws, void *stream);
+int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
+                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, int overlapping,
+                   int codepoints, const acb_workspace *ws, void *stream);
 
 /*
  * Scan ONE large device-resident haystack, split into fixed-size chunks that
@@ -146,8 +166,9 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const uint8_t 
  * Units are chunks: acb_chunk_count(len, chunk_bytes).
  */
 uint64_t acb_chunk_count(uint64_t len, uint32_t chunk_bytes);
-int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, uint64_t len,
-                     uint32_t chunk_bytes, int codepoints, const acb_workspace *ws, void *stream);
+int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
+                     const uint8_t *dev_bytes, uint64_t len, uint32_t chunk_bytes, int codepoints,
+                     const acb_workspace *ws, void *stream);
 
 /* Kernel launch bookkeeping for bench.py's "gpu_launches". */
 uint64_t acb_launch_count(void);

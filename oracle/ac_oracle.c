@@ -66,6 +66,9 @@ typedef struct orc_ac {
     uint8_t classes[256];
     uint32_t ncls, stride;
     uint32_t *trans; /* nstates * stride, entries are state ids */
+    /* the same table the way the crate's DFA stores it for speed: ids premultiplied
+     * by the stride, match states recognisable without a second lookup (here: top bit) */
+    uint32_t *ftrans;
 } orc_ac;
 
 static void *xrealloc(void *p, size_t n) {
@@ -155,6 +158,7 @@ void orc_free(orc_ac *a) {
     free(a->mlist);
     free(a->pat_len);
     free(a->trans);
+    free(a->ftrans);
     free(a);
 }
 
@@ -269,6 +273,11 @@ orc_ac *orc_build(const uint8_t *blob, const uint64_t *offs, uint64_t n, int kin
         if (s == ORC_FAIL) continue;
         for (uint32_t c = 0; c < a->ncls; c++) a->trans[(uint64_t)s * a->stride + c] = nfa_next(a, s, rep[c]);
     }
+    a->ftrans = calloc(cells, sizeof(uint32_t));
+    for (uint64_t i = 0; i < cells; i++) {
+        uint32_t t = a->trans[i];
+        a->ftrans[i] = (t * a->stride) | (a->first_match[t] ? 0x80000000u : 0u);
+    }
     return a;
 }
 
@@ -290,8 +299,42 @@ static inline uint32_t step(const orc_ac *a, int use_dfa, uint32_t s, uint8_t b)
 int64_t orc_find_iter(const orc_ac *a, const uint8_t *hay, uint64_t len, int overlapping, int use_dfa,
                       uint32_t *out_pid, uint64_t *out_start, uint64_t *out_end, uint64_t cap) {
     uint64_t n = 0;
+    if (overlapping && a->kind != ORC_STANDARD) return -1;
+    if (use_dfa && !overlapping) {
+        /* same loop as below on the premultiplied, flagged table (what the timed baseline runs) */
+        const uint32_t *T = a->ftrans;
+        const uint8_t *cls = a->classes;
+        const uint32_t root = ORC_START * a->stride;
+        uint64_t start = 0;
+        while (start <= len) {
+            uint32_t sid = root;
+            int have = 0;
+            uint32_t mpid = 0;
+            uint64_t mend = 0;
+            for (uint64_t at = start; at < len; at++) {
+                uint32_t e = T[sid + cls[hay[at]]];
+                sid = e & 0x7fffffffu;
+                if (e >> 31) {
+                    have = 1;
+                    mpid = a->mlist[a->first_match[sid / a->stride]].pid;
+                    mend = at + 1;
+                    if (a->kind == ORC_STANDARD) break;
+                } else if (sid == ORC_DEAD) {
+                    break;
+                }
+            }
+            if (!have) break;
+            if (n < cap) {
+                out_pid[n] = mpid;
+                out_start[n] = mend - a->pat_len[mpid];
+                out_end[n] = mend;
+            }
+            n++;
+            start = mend;
+        }
+        return (int64_t)n;
+    }
     if (overlapping) {
-        if (a->kind != ORC_STANDARD) return -1;
         uint32_t sid = ORC_START;
         for (uint64_t at = 0; at < len; at++) {
             sid = step(a, use_dfa, sid, hay[at]);
@@ -363,6 +406,7 @@ typedef struct {
     uint32_t *rec; /* 4 x u32 per match: hay, pid, start, end */
     uint64_t rec_cap, nrec;
     uint64_t total;
+    int reps; /* timing only: scan the shard this many times inside one thread launch */
 } orc_job;
 
 static void *batch_worker(void *arg) {
@@ -372,6 +416,7 @@ static void *batch_worker(void *arg) {
     uint64_t st[64], en[64];
     uint64_t *b2c = NULL;
     uint64_t b2c_cap = 0;
+    for (int rep = 0; rep < j->reps; rep++)
     for (int64_t h = j->lo; h < j->hi; h++) {
         const uint8_t *hay = j->bytes + j->offs[h];
         uint64_t len = (uint64_t)(j->offs[h + 1] - j->offs[h]);
@@ -429,8 +474,21 @@ static void *batch_worker(void *arg) {
  * NULL.  Records come back in haystack order, then iteration order.  Returns
  * the total number of matches.
  */
+uint64_t orc_scan_batch_reps(const orc_ac *a, const uint8_t *bytes, const int64_t *offs, int64_t n, int overlapping,
+                             int codepoints, int nthreads, uint32_t *counts, uint32_t *rec, uint64_t rec_cap, int reps);
+
 uint64_t orc_scan_batch(const orc_ac *a, const uint8_t *bytes, const int64_t *offs, int64_t n, int overlapping,
                         int codepoints, int nthreads, uint32_t *counts, uint32_t *rec, uint64_t rec_cap) {
+    return orc_scan_batch_reps(a, bytes, offs, n, overlapping, codepoints, nthreads, counts, rec, rec_cap, 1);
+}
+
+/* Same, with every thread scanning its shard `reps` times (the CPU-baseline
+ * timing loop: keeps thread start-up out of the measurement).  The returned
+ * total counts every repetition. */
+uint64_t orc_scan_batch_reps(const orc_ac *a, const uint8_t *bytes, const int64_t *offs, int64_t n, int overlapping,
+                             int codepoints, int nthreads, uint32_t *counts, uint32_t *rec, uint64_t rec_cap, int reps) {
+    if (reps < 1) reps = 1;
+    if (rec) reps = 1;
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if (rec) nthreads = 1; /* ordered records: keep it simple, single writer */
@@ -440,7 +498,7 @@ uint64_t orc_scan_batch(const orc_ac *a, const uint8_t *bytes, const int64_t *of
     int64_t total_bytes = offs[n] - offs[0];
     int64_t h = 0;
     for (int t = 0; t < nthreads; t++) {
-        jobs[t] = (orc_job){a, bytes, offs, h, h, overlapping, codepoints, counts, rec, rec_cap, 0, 0};
+        jobs[t] = (orc_job){a, bytes, offs, h, h, overlapping, codepoints, counts, rec, rec_cap, 0, 0, reps};
         int64_t target = offs[0] + (total_bytes * (t + 1)) / nthreads;
         while (h < n && (offs[h + 1] <= target || t == nthreads - 1)) h++;
         jobs[t].hi = h;

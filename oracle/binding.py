@@ -50,6 +50,8 @@ def _load():
         lib.orc_scan_batch.restype = c.c_uint64
         lib.orc_scan_batch.argtypes = [c.c_void_p, c.c_void_p, c.c_void_p, c.c_int64, c.c_int, c.c_int,
                                        c.c_int, c.c_void_p, c.c_void_p, c.c_uint64]
+        lib.orc_scan_batch_reps.restype = c.c_uint64
+        lib.orc_scan_batch_reps.argtypes = lib.orc_scan_batch.argtypes + [c.c_int]
         _lib = lib
     return _lib
 
@@ -110,6 +112,15 @@ class Oracle:
         b2c = np.empty(len(raw) + 1, dtype=np.uint64)
         lib.orc_byte_to_code_point(hay.ctypes.data, len(raw), b2c.ctypes.data)
         return [(p, int(b2c[s]), int(b2c[e])) for (p, s, e) in self.find(raw, overlapping, use_dfa)]
+
+    def time_batch(self, data: np.ndarray, offsets: np.ndarray, overlapping=False, codepoints=False, nthreads=1, reps=1):
+        """Timing helper: every thread scans its contiguous shard `reps` times. -> total matches over all reps."""
+        lib = _load()
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        n = len(offsets) - 1
+        return int(lib.orc_scan_batch_reps(self._h, data.ctypes.data, offsets.ctypes.data, n, int(overlapping),
+                                           int(codepoints), int(nthreads), None, None, 0, int(reps)))
 
     def scan_batch(self, data: np.ndarray, offsets: np.ndarray, overlapping=False, codepoints=False,
                    nthreads=1, want_records=True, rec_cap=None):

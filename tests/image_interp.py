@@ -36,7 +36,7 @@ class Image:
         n = L.acb_image_bytes(h)
         buf = np.zeros(n, dtype=np.uint8)
         assert L.acb_image_write(h, buf.ctypes.data, n) == 0
-        L.acb_free(h)
+        self._h = h
         self.raw = buf
         f = struct.unpack_from(HDR_FMT, buf.tobytes()[: struct.calcsize(HDR_FMT)])
         (self.magic, self.version, self.kind, self.col_mode, self.n_states, self.n_cols, self.col_lo, self.n_patterns,
@@ -55,15 +55,31 @@ class Image:
             return min((b - self.col_lo) & 0xFFFFFFFF, self.n_cols - 1)
         return int(self.colmap[b])
 
-    def hot_table(self, H):
-        """scan_staged_kernel prologue."""
-        hot = np.full((H + 1, self.n_cols), H, dtype=np.uint32)
-        for s in range(1, min(H, self.n_states)):
-            e = self.trans[s]
-            t = e & MASK
-            ok = ((e & FLAG) == 0) & (t != K_DEAD) & (t < H)
-            hot[s] = np.where(ok, t, H)
-        return hot
+    def hot_image(self, visits=None, max_rows=4096):
+        """acb_hot_build -> (table[(rows+1), n_cols], hot2full, full2hot, rows)."""
+        L = _capi.lib()
+        n = L.acb_hot_bytes(self._h, max_rows)
+        buf = np.zeros(n, dtype=np.uint8)
+        vp = None
+        if visits is not None:
+            visits = np.ascontiguousarray(visits, dtype=np.uint32)
+            vp = visits.ctypes.data
+        assert L.acb_hot_build(self._h, vp, max_rows, buf.ctypes.data, n) == 0
+        rows = L.acb_hot_rows(buf.ctypes.data)
+        magic, n_rows, n_cols, n_states, o_table, o_h2f, o_f2h, total = struct.unpack_from("<4I4Q", buf.tobytes()[:48])
+        assert magic == 0x31424341 and n_rows == rows and n_cols == self.n_cols and total == n
+        table = buf[o_table:o_table + 2 * (rows + 1) * n_cols].view(np.uint16).reshape(rows + 1, n_cols)
+        h2f = buf[o_h2f:o_h2f + 4 * (rows + 1)].view(np.uint32)
+        f2h = buf[o_f2h:o_f2h + 2 * n_states].view(np.uint16)
+        return table, h2f, f2h, rows
+
+    def hot_table(self, H, visits=None):
+        """scan_staged_kernel prologue: the first H rows of the hot image, clamped to H."""
+        table, h2f, f2h, rows = self.hot_image(visits)
+        H = min(H, rows)
+        hot = np.minimum(table[: H + 1].astype(np.uint32), H)
+        hot[H, :] = H
+        return hot, h2f, f2h, H
 
 
 class Ctx:
@@ -92,7 +108,7 @@ def report(c, im, pid, end):
     c.out.append((int(pid), start, end))
 
 
-def exact_scan(c, im, mode, stop_hot=False, min_at=0, phase=0, hot_limit=0):
+def exact_scan(c, im, mode, stop_hot=False, min_at=0, phase=0, hot_limit=0, f2h=None):
     s, at, end = c.state, c.at, c.end
     while True:
         if mode == 1:
@@ -108,8 +124,8 @@ def exact_scan(c, im, mode, stop_hot=False, min_at=0, phase=0, hot_limit=0):
                 s = K_ROOT
         elif at == end:
             break
-        if (stop_hot and at >= min_at and ((at - phase) & 15) == 0 and s < hot_limit and s != K_DEAD
-                and (mode != 1 or not c.have)):
+        if (stop_hot and at >= min_at and ((at - phase) & 15) == 0 and (mode != 1 or not c.have)
+                and int(f2h[s]) < hot_limit):
             break
         e = int(im.trans[s, im.col(c.hay[at])])
         s = e & MASK
@@ -133,20 +149,21 @@ def cp_catch_up(c, to):
         c.cp_pos += 1
 
 
-def staged_lane(im, hay: bytes, mode, H, base_addr=0, at=0, end=None, emit_from=0, cp=False, hot=None, stats=None):
+def staged_lane(im, hay: bytes, mode, H, base_addr=0, at=0, end=None, emit_from=0, cp=False, hot=None, stats=None,
+                visits=None):
     """One lane of scan_staged_kernel over hay[at:end]; base_addr = absolute
     address of hay[0] (only its low bits matter: 16-byte group alignment)."""
     end = len(hay) if end is None else end
     c = Ctx(hay, at, end, emit_from, cp)
-    hot = im.hot_table(H) if hot is None else hot
+    hot, h2f, f2h, H = im.hot_table(H, visits) if hot is None else hot
     phase = (-base_addr) & 15
     p0 = base_addr + at
     a0 = p0 & ~63
     pe = base_addr + end
     nchunks = (pe - a0 + 63) // 64 if pe > a0 else 0
     rel0 = at - (p0 - a0)
-    exact_scan(c, im, mode, True, c.at, phase, H)
-    pos, s = c.at, c.state
+    exact_scan(c, im, mode, True, c.at, phase, H, f2h)
+    pos, s = c.at, int(f2h[c.state])
     if cp:
         cp_catch_up(c, pos)
     for k in range(nchunks):
@@ -171,13 +188,14 @@ def staged_lane(im, hay: bytes, mode, H, base_addr=0, at=0, end=None, emit_from=
                 else:
                     if stats is not None:
                         stats["traps"] = stats.get("traps", 0) + 1
-                    c.state, c.at = s, pos
-                    exact_scan(c, im, mode, True, pos + 16, phase, H)
-                    s, pos = c.state, c.at
+                    c.state, c.at = int(h2f[s]), pos
+                    exact_scan(c, im, mode, True, pos + 16, phase, H, f2h)
+                    s, pos = int(f2h[c.state]), c.at
                     if cp:
                         cp_catch_up(c, pos)
-    c.state, c.at = s, pos
-    exact_scan(c, im, mode)
+    if pos < c.end:
+        c.state, c.at = int(h2f[s]), pos
+        exact_scan(c, im, mode)
     return c.out
 
 

@@ -135,6 +135,32 @@ def test_names_automaton_shape_and_parity():
         assert ii.staged_lane(im2, line, 1, 1500) == Oracle(pats, kind).find(line)
 
 
+def test_profiled_hot_set_keeps_results_and_cuts_traps():
+    import struct
+    from ahocorasick_rs_b200 import workloads as W
+    pats, data, offs = W.config2(3)
+    bp = [p.encode() for p in pats]
+    im = ii.Image(bp, 0, 2)
+    hay = bytes(data[offs[1]:offs[2]])
+    # visit counts as acb_profile would produce them from haystack 0
+    visits = np.zeros(im.n_states, dtype=np.uint32)
+    s = 1
+    for b in bytes(data[offs[0]:offs[1]]):
+        e = int(im.trans[s, im.col(b)])
+        s = e & ii.MASK
+        if e & ii.FLAG:
+            s = 1
+        visits[s] += 1
+    exp = Oracle(bp, "Standard").find_str(hay.decode())
+    st_bfs, st_prof = {}, {}
+    assert ii.staged_lane(im, hay, 0, 256, cp=True, stats=st_bfs) == exp
+    assert ii.staged_lane(im, hay, 0, 256, cp=True, stats=st_prof, visits=visits) == exp
+    assert st_prof.get("traps", 0) * 20 < st_bfs["traps"]      # 256 profiled rows beat 256 shallowest rows by far
+    table, h2f, f2h, rows = im.hot_image(visits, 300)
+    assert rows == 300 and h2f[0] == 1 and f2h[1] == 0 and f2h[0] == 0xFFFF
+    assert len(set(h2f[:rows].tolist())) == rows and all(f2h[h2f[i]] == i for i in range(rows))
+
+
 def test_builder_errors():
     with pytest.raises(ValueError):
         ii.Image([b"a", b""])
