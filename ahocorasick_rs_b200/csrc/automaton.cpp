@@ -293,7 +293,9 @@ Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_
 static uint32_t hot_rows_for(const Automaton &a, uint32_t max_rows) {
     uint32_t H = max_rows;
     if (H > a.hdr.n_states - 1) H = a.hdr.n_states - 1;  // kDead is never hot
-    if (H > 65534) H = 65534;
+    // entries are u16 BYTE offsets of rows (hot index * row bytes), so the trap row must start below 64 KiB
+    const uint32_t by_offset = 65535u / (a.hdr.n_cols * 2u);
+    if (H > by_offset) H = by_offset;
     if (H < 1) H = 1;
     return H;
 }
@@ -354,17 +356,18 @@ void build_hot_image(const Automaton &a, const uint32_t *visits, uint32_t max_ro
     // n == H here because H <= n_states - 1
 
     const uint32_t *T = reinterpret_cast<const uint32_t *>(a.image.data() + ih.off_trans);
+    const uint32_t row_bytes = n_cols * 2;
     for (uint32_t h = 0; h < H; h++) {
         const uint32_t *row = T + uint64_t(hot2full[h]) * n_cols;
         uint16_t *out = table + uint64_t(h) * n_cols;
         for (uint32_t c = 0; c < n_cols; c++) {
             const uint32_t e = row[c], t = e & kStateMask;
-            uint16_t v = static_cast<uint16_t>(H);
+            uint32_t v = H;
             if (!(e & kMatchFlag) && t != kDead && full2hot[t] != kNotHot) v = full2hot[t];
-            out[c] = v;
+            out[c] = static_cast<uint16_t>(v * row_bytes);
         }
     }
-    for (uint32_t c = 0; c < n_cols; c++) table[uint64_t(H) * n_cols + c] = static_cast<uint16_t>(H);
+    for (uint32_t c = 0; c < n_cols; c++) table[uint64_t(H) * n_cols + c] = static_cast<uint16_t>(H * row_bytes);
     hot2full[H] = kDead;
 }
 

@@ -49,13 +49,15 @@ constexpr uint32_t kImageMagic = 0x30424341u;  // "ACB0"
 // The hot image: the part of the automaton the staged kernel keeps in shared
 // memory.  Rows are ordered hottest first (by sampled visit counts, the root
 // always first, then shallow states as filler), so a kernel that can only fit
-// H' < n_rows rows takes a prefix.  Entries are HOT INDICES; n_rows = trap.
+// H' < n_rows rows takes a prefix.  Table entries are the BYTE OFFSET of the next
+// state's row inside the table (hot index * n_cols * 2, so one add forms the
+// shared-memory address); n_rows * n_cols * 2 = the trap row.
 struct HotHeader {
     uint32_t magic;
     uint32_t n_rows;    // H
     uint32_t n_cols;
     uint32_t n_states;
-    uint64_t off_table;     // u16[(H + 1) * n_cols]; row H is all H
+    uint64_t off_table;     // u16[(H + 1) * n_cols]; row H (the trap row) maps everything to itself
     uint64_t off_hot2full;  // u32[H + 1]
     uint64_t off_full2hot;  // u16[n_states]; 0xffff = not hot
     uint64_t total_bytes;

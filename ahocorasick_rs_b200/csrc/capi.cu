@@ -351,14 +351,14 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Units &U, const S
     const uint32_t row_bytes = im.n_cols * 2;
     const uint32_t stage_bytes = (uint32_t)warps * 2 * kStageBytes;
     const uint32_t budget = (uint32_t)d.max_smem_optin;
-    if (budget < stage_bytes + 256 + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
-    uint32_t rows = (budget - stage_bytes - 256 - 128) / row_bytes;  // includes the trap row
+    if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
+    uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
     uint32_t H = rows - 1;
     if (H > hot.n_rows) H = hot.n_rows;
     if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
     if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
     const uint32_t hot_bytes = (((H + 1) * row_bytes) + 127u) & ~127u;
-    const uint32_t smem = hot_bytes + 256 + stage_bytes;
+    const uint32_t smem = hot_bytes + kStageOffset + stage_bytes;
     static thread_local int configured_for = -1;
     (void)configured_for;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));

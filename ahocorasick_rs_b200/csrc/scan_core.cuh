@@ -188,8 +188,14 @@ __device__ __forceinline__ bool init_unit(UnitCtx &c, const Units &U, int64_t u)
         c.end = (uint32_t)hi;
         c.emit_from = (uint32_t)lo;
         c.hay = 0;
-        c.cp_pos = (uint32_t)lo;
-        c.cp_count = CP ? (uint32_t)U.chunk_cp[u] : 0;
+        // code points before the first byte this unit READS (the halo starts before the chunk)
+        c.cp_pos = c.at;
+        c.cp_count = 0;
+        if (CP) {
+            uint32_t n = (uint32_t)U.chunk_cp[u];
+            for (uint32_t p = c.at; p < (uint32_t)lo; p++) n -= (ld_u8(c.base + p) & 0xC0u) != 0x80u;
+            c.cp_count = n;
+        }
     }
     return true;
 }

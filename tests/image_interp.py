@@ -77,7 +77,9 @@ class Image:
         """scan_staged_kernel prologue: the first H rows of the hot image, clamped to H."""
         table, h2f, f2h, rows = self.hot_image(visits)
         H = min(H, rows)
-        hot = np.minimum(table[: H + 1].astype(np.uint32), H)
+        row_bytes = 2 * self.n_cols
+        assert np.all(table % row_bytes == 0) and table.max() == rows * row_bytes  # byte offsets of rows; trap = last row
+        hot = np.minimum(table[: H + 1].astype(np.uint32) // row_bytes, H)
         hot[H, :] = H
         return hot, h2f, f2h, H
 
@@ -90,7 +92,7 @@ class Ctx:
         self.have = False
         self.last_pid = self.last_end = 0
         self.cp = cp
-        self.cp_pos = emit_from
+        self.cp_pos = at          # init_unit: counting starts at the first byte the unit reads
         self.cp_count = 0
         self.out = []
 
@@ -164,8 +166,10 @@ def staged_lane(im, hay: bytes, mode, H, base_addr=0, at=0, end=None, emit_from=
     rel0 = at - (p0 - a0)
     exact_scan(c, im, mode, True, c.at, phase, H, f2h)
     pos, s = c.at, int(f2h[c.state])
+    cpd = 0
     if cp:
         cp_catch_up(c, pos)
+        cpd = pos - c.cp_count
     for k in range(nchunks):
         relk = rel0 + 64 * k
         for j in range(4):
@@ -179,22 +183,23 @@ def staged_lane(im, hay: bytes, mode, H, base_addr=0, at=0, end=None, emit_from=
                 if t != H:
                     s = t
                     if cp:
-                        if c.cp_pos == pos:
-                            c.cp_count += sum((b & 0xC0) != 0x80 for b in hay[pos:pos + 16])
-                            c.cp_pos = pos + 16
-                        else:
-                            cp_catch_up(c, pos + 16)
+                        cpd += sum((b & 0xC0) == 0x80 for b in hay[pos:pos + 16])
                     pos += 16
                 else:
                     if stats is not None:
                         stats["traps"] = stats.get("traps", 0) + 1
                     c.state, c.at = int(h2f[s]), pos
+                    if cp:
+                        c.cp_pos, c.cp_count = pos, pos - cpd
                     exact_scan(c, im, mode, True, pos + 16, phase, H, f2h)
                     s, pos = int(f2h[c.state]), c.at
                     if cp:
                         cp_catch_up(c, pos)
+                        cpd = pos - c.cp_count
     if pos < c.end:
         c.state, c.at = int(h2f[s]), pos
+        if cp:
+            c.cp_pos, c.cp_count = pos, pos - cpd
         exact_scan(c, im, mode)
     return c.out
 
@@ -216,14 +221,15 @@ def find_chunked(im, hay: bytes, chunk, H=None, cp=False, base_addr=0):
     for u in range(n):
         lo, hi = u * chunk, min((u + 1) * chunk, len(hay))
         at = lo - halo if lo > halo else 0
+        cps_at = cps - sum((b & 0xC0) != 0x80 for b in hay[at:lo])
         if H is None:
             c = Ctx(hay, at, hi, lo, cp)
-            c.cp_count = cps
+            c.cp_count = cps_at
             exact_scan(c, im, 2)
             out += c.out
         else:
             # staged lane with pre-seeded code point count
-            res = _staged_chunk(im, hay, H, base_addr, at, hi, lo, cp, cps)
+            res = _staged_chunk(im, hay, H, base_addr, at, hi, lo, cp, cps_at)
             out += res
         cps += sum((b & 0xC0) != 0x80 for b in hay[lo:hi])
     return out
