@@ -13,17 +13,24 @@ ACB_OK = 0
 ACB_EINVAL, ACB_EBUILD, ACB_EUNSUPPORTED, ACB_ECUDA, ACB_ECAPACITY = -1, -2, -3, -4, -5
 
 
+class Plan(C.Structure):
+    _fields_ = [("n_segments", C.c_uint64), ("n_units", C.c_uint64), ("scratch_words", C.c_uint64),
+                ("segment_bytes", C.c_uint32), ("warm_bytes", C.c_uint32), ("lane_stride", C.c_uint32),
+                ("reserved", C.c_uint32)]
+
+
 class Workspace(C.Structure):
     _fields_ = [
-        ("dev_raw", C.c_void_p), ("dev_raw_seq", C.c_void_p), ("dev_raw_unit", C.c_void_p),
+        ("dev_raw", C.c_void_p), ("dev_raw_seq", C.c_void_p), ("dev_raw_unit", C.c_void_p), ("dev_raw_aux", C.c_void_p),
         ("raw_capacity", C.c_uint64),
-        ("dev_unit_counts", C.c_void_p), ("dev_unit_offsets", C.c_void_p), ("dev_scratch", C.c_void_p),
-        ("dev_total", C.c_void_p), ("dev_out", C.c_void_p), ("out_capacity", C.c_uint64),
+        ("dev_unit_counts", C.c_void_p), ("dev_unit_offsets", C.c_void_p), ("dev_seg_info", C.c_void_p),
+        ("dev_scratch", C.c_void_p), ("dev_total", C.c_void_p), ("dev_out", C.c_void_p), ("out_capacity", C.c_uint64),
+        ("dev_match_offsets", C.c_void_p),
     ]
 
 
 class Tuning(C.Structure):
-    _fields_ = [("kernel", C.c_int), ("hot_rows", C.c_int), ("ctas_per_sm", C.c_int)]
+    _fields_ = [("kernel", C.c_int), ("hot_rows", C.c_int), ("segment_bytes", C.c_int), ("reserved", C.c_int)]
 
 
 _lib = None
@@ -55,10 +62,7 @@ def lib():
             fn.restype = res
             fn.argtypes = [C.c_void_p]
         L.acb_image_write.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
-        L.acb_scratch_words.restype = C.c_uint64
-        L.acb_scratch_words.argtypes = [C.c_uint64]
-        L.acb_chunk_count.restype = C.c_uint64
-        L.acb_chunk_count.argtypes = [C.c_uint64, C.c_uint32]
+        L.acb_plan_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(Plan)]
         L.acb_profile.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int,
                                   C.c_void_p, C.c_void_p]
         L.acb_hot_bytes.restype = C.c_uint64
@@ -67,9 +71,7 @@ def lib():
         L.acb_hot_rows.restype = C.c_uint32
         L.acb_hot_rows.argtypes = [C.c_void_p]
         L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64,
-                                     C.c_int, C.c_int, C.POINTER(Workspace), C.c_void_p]
-        L.acb_scan_chunked.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
-                                       C.c_uint32, C.c_int, C.POINTER(Workspace), C.c_void_p]
+                                     C.c_uint64, C.c_int, C.c_int, C.POINTER(Plan), C.POINTER(Workspace), C.c_void_p]
         _lib = L
     return _lib
 
@@ -81,7 +83,7 @@ def last_error() -> str:
 EXPORTS = [
     "acb_last_error", "acb_version", "acb_build", "acb_free", "acb_num_patterns", "acb_num_states",
     "acb_num_columns", "acb_max_pattern_len", "acb_min_pattern_len", "acb_match_kind", "acb_image_bytes",
-    "acb_image_write", "acb_scratch_words", "acb_scan_batch", "acb_chunk_count", "acb_scan_chunked",
+    "acb_image_write", "acb_plan_scan", "acb_scan_batch",
     "acb_launch_count", "acb_set_tuning", "acb_timing_enable", "acb_timing_read",
     "acb_profile", "acb_hot_bytes", "acb_hot_build", "acb_hot_rows",
 ]

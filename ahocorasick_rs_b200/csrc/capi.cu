@@ -1,4 +1,4 @@
-// capi.cu -- the C ABI (include/acb200.h): kernel dispatch + ordering passes.
+// capi.cu -- the C ABI (include/acb200.h): planning, kernel dispatch, ordering passes.
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -6,20 +6,36 @@
 #include <utility>
 #include <vector>
 
+#include "repair.cuh"
 #include "scan_staged.cuh"
 
 namespace acb {
 
 // ---------------------------------------------------------------------------
-// plain kernel: the exact scanner over whole units, table in global memory
+// plain kernel: the exact scanner over whole haystacks, table in global memory
+// (units = haystacks; used when no hot image is given, and as the cross-check
+// of the staged + repair path in the tests)
 // ---------------------------------------------------------------------------
 template <int MODE, bool CP>
-__global__ void __launch_bounds__(128) scan_plain_kernel(DevImage im, Units U, Sink out) {
-    for (int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; u < U.n_units; u += (int64_t)gridDim.x * blockDim.x) {
-        UnitCtx c;
-        init_unit<CP>(c, U, u);
+__global__ void __launch_bounds__(128) scan_plain_kernel(DevImage im, Batch B, Sink out) {
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t hs = B.offsets[h], he = B.offsets[h + 1];
+        PieceCtx c;
+        c.base = B.bytes + hs;
+        c.at = 0;
+        c.stop = c.limit = (uint32_t)(he - hs);
+        c.emit_from = 0;
+        c.state = kRoot;
+        c.have = 0;
+        c.last_pid = c.last_end = 0;
+        c.hay = (uint32_t)h;
+        c.hay_delta = 0;
+        c.unit = (uint32_t)h;
+        c.nemit = 0;
+        c.cp_pos = 0;
+        c.cp_cont = 0;
         exact_scan<MODE, CP>(c, im, out, false, 0, 0, HotMap{nullptr, 0});
-        out.unit_counts[u] = c.nemit;
+        out.unit_counts[h] = c.nemit;
     }
 }
 
@@ -29,20 +45,16 @@ __global__ void __launch_bounds__(128) scan_plain_kernel(DevImage im, Units U, S
 // the staged kernel keeps in shared memory (automaton.cpp: build_hot_image)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-profile_kernel(DevImage im, Units U, uint32_t *visits, int64_t n_samples, uint32_t max_bytes, int restart_on_match) {
+profile_kernel(DevImage im, Batch B, uint32_t *visits, int64_t n_samples, uint32_t max_bytes, int restart_on_match) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_samples) return;
-    const uint8_t *p;
-    uint64_t len;
-    if (U.chunk == 0) {
-        const int64_t u = (U.n_units * i) / n_samples;
-        p = U.bytes + U.offsets[u];
-        len = (uint64_t)(U.offsets[u + 1] - U.offsets[u]);
-    } else {
-        const uint64_t lo = (U.len / (uint64_t)n_samples) * (uint64_t)i;
-        p = U.bytes + lo;
-        len = U.len - lo;
-    }
+    // sample i reads max_bytes at stream position lo + i * (len / n_samples), staying inside one haystack
+    const int64_t lo = B.offsets[0], hi = B.offsets[B.n_haystacks];
+    if (hi <= lo) return;
+    const int64_t p0 = lo + ((hi - lo) / n_samples) * i;
+    const int64_t h = find_haystack(B, p0);
+    const uint8_t *p = B.bytes + p0;
+    uint64_t len = (uint64_t)(B.offsets[h + 1] - p0);
     if (len > max_bytes) len = max_bytes;
     uint32_t s = kRoot;
     for (uint64_t k = 0; k < len; k++) {
@@ -54,7 +66,7 @@ profile_kernel(DevImage im, Units U, uint32_t *visits, int64_t n_samples, uint32
 }
 
 // ---------------------------------------------------------------------------
-// exclusive prefix sum u32[n] -> u64[n+1] (three small kernels)
+// exclusive prefix sum u32[n] (strided) -> u64[n+1] (three small kernels)
 // ---------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -87,12 +99,14 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return before + x - v;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums(const uint32_t *in, uint64_t n, unsigned long long *tile_sums) {
+// in[i * stride] for i in [0, n)
+__global__ void __launch_bounds__(kScanThreads)
+scan_tile_sums(const uint32_t *in, uint32_t stride, uint64_t n, unsigned long long *tile_sums) {
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     unsigned long long v = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++)
-        if (base + i < n) v += in[base + i];
+        if (base + i < n) v += in[(base + i) * stride];
     unsigned long long total;
     block_exclusive_scan(v, &total);
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
@@ -111,12 +125,12 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(unsigned long 
 }
 
 __global__ void __launch_bounds__(kScanThreads)
-scan_apply(const uint32_t *in, uint64_t n, const unsigned long long *tile_offs, unsigned long long *out) {
+scan_apply(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long long *tile_offs, unsigned long long *out) {
     const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     unsigned long long vals[kScanItems], v = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
-        vals[i] = base + i < n ? in[base + i] : 0;
+        vals[i] = base + i < n ? in[(base + i) * stride] : 0;
         v += vals[i];
     }
     unsigned long long total;
@@ -129,39 +143,93 @@ scan_apply(const uint32_t *in, uint64_t n, const unsigned long long *tile_offs, 
     }
 }
 
-// final placement: match i of unit u with rank r goes to unit_offsets[u] + r
-__global__ void __launch_bounds__(256)
-order_matches_kernel(const acb_match *raw, const uint32_t *raw_seq, const uint32_t *raw_unit, unsigned long long raw_cap,
-                     const unsigned long long *total, const unsigned long long *unit_offsets, acb_match *out,
-                     unsigned long long out_cap) {
-    unsigned long long n = *total;
-    if (n > raw_cap) n = raw_cap;
+// ---------------------------------------------------------------------------
+// final placement: raw match i of unit u with rank r goes to unit_offsets[u] + r
+// (segments: minus the matches the repair pass superseded); code point fix-up
+// ---------------------------------------------------------------------------
+struct OrderArgs {
+    const acb_match *raw;
+    const uint32_t *raw_seq, *raw_unit, *raw_aux;
+    unsigned long long raw_cap;
+    const unsigned long long *raw_total;
+    const unsigned long long *unit_offsets;
+    const SegInfo *seg_info;             // null: units are haystacks (plain kernel)
+    const unsigned long long *cont_cum;  // exclusive prefix sum of SegInfo.cont_tail (code points + segments)
+    const int64_t *hay_offsets;
+    const uint32_t *pat_cplen;
+    int64_t origin;
+    uint32_t seg_bytes;
+    int codepoints;
+    acb_match *out;
+    unsigned long long out_cap;
+};
+
+__global__ void __launch_bounds__(256) order_matches_kernel(OrderArgs A) {
+    unsigned long long n = *A.raw_total;
+    if (n > A.raw_cap) n = A.raw_cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (unsigned long long)gridDim.x * blockDim.x) {
-        const unsigned long long dst = unit_offsets[raw_unit[i]] + raw_seq[i];
-        if (dst < out_cap) reinterpret_cast<uint4 *>(out)[dst] = reinterpret_cast<const uint4 *>(raw)[i];
+        const uint32_t u = A.raw_unit[i];
+        uint32_t seq = A.raw_seq[i];
+        if (A.seg_info && (u & 1u)) {
+            const uint32_t drop = A.seg_info[u >> 1].drop;
+            if (seq < drop) continue;  // superseded by the repair pass
+            seq -= drop;
+        }
+        const unsigned long long dst = A.unit_offsets[u] + seq;
+        if (dst >= A.out_cap) continue;
+        uint4 r = reinterpret_cast<const uint4 *>(A.raw)[i];  // haystack, pattern, start, end (bytes)
+        if (A.codepoints) {
+            unsigned long long cont = A.raw_aux[i];  // continuation bytes from the counting origin to the match end
+            if (A.seg_info) {
+                const int64_t j = u >> 1;
+                const int64_t hs = A.hay_offsets[r.x];
+                if (hs < A.origin + j * (int64_t)A.seg_bytes) {
+                    // the match's haystack began in an earlier segment: add what those segments counted
+                    const int64_t j0 = (hs - A.origin) / (int64_t)A.seg_bytes;
+                    cont += A.cont_cum[j] - A.cont_cum[j0];
+                }
+            }
+            const uint32_t end_cp = r.w - (uint32_t)cont;
+            r.w = end_cp;
+            r.z = end_cp - A.pat_cplen[r.y];
+        }
+        reinterpret_cast<uint4 *>(A.out)[dst] = r;
     }
 }
 
-__global__ void finish_total_kernel(unsigned long long *total, unsigned long long raw_cap, unsigned long long out_cap) {
-    const unsigned long long n = total[0];
-    total[1] = (n <= raw_cap && n <= out_cap) ? n : 0;  // [1] = matches delivered in dev_out (0 = incomplete, retry)
+// per-haystack CSR offsets into the ordered output (binary search per haystack) + the totals
+__global__ void __launch_bounds__(256)
+match_offsets_kernel(const acb_match *out, const unsigned long long *unit_offsets, uint64_t n_units, unsigned long long *totals,
+                     unsigned long long raw_cap, unsigned long long out_cap, int64_t n_haystacks, unsigned long long *match_offsets) {
+    const unsigned long long total = unit_offsets[n_units];
+    const unsigned long long avail = total < out_cap ? total : out_cap;
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long lo = 0, hi = avail;  // first index whose haystack >= h
+        while (lo < hi) {
+            const unsigned long long mid = (lo + hi) >> 1;
+            if ((int64_t)out[mid].haystack < h)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        match_offsets[h] = (h == n_haystacks) ? total : lo;
+        if (h == 0) {
+            totals[0] = total;
+            totals[1] = (totals[4] <= raw_cap && total <= out_cap) ? 1 : 0;  // complete?
+        }
+    }
 }
 
-// code points (non-continuation bytes) per chunk, for the chunked scan with codepoints
-__global__ void __launch_bounds__(256) chunk_cp_count_kernel(const uint8_t *bytes, uint64_t len, uint32_t chunk, uint32_t *counts, uint64_t n_chunks) {
-    // one warp per chunk
-    const uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const uint32_t lane = threadIdx.x & 31;
-    if (warp >= n_chunks) return;
-    const uint64_t lo = warp * chunk;
-    uint64_t hi = lo + chunk;
-    if (hi > len) hi = len;
-    uint32_t n = 0;
-    for (uint64_t p = lo + lane; p < hi; p += 32) n += (__ldg(bytes + p) & 0xC0u) != 0x80u;
-#pragma unroll
-    for (int d = 16; d; d >>= 1) n += __shfl_xor_sync(0xffffffffu, n, d);
-    if (lane == 0) counts[warp] = n;
+__global__ void clear_totals_kernel(unsigned long long *totals, unsigned int *task_counter) {
+    if (threadIdx.x < 8) totals[threadIdx.x] = 0;
+    if (threadIdx.x == 0) *task_counter = 0;
+}
+
+// when the input is empty: nothing ran, publish zeros
+__global__ void zero_outputs_kernel(unsigned long long *unit_offsets, unsigned long long *match_offsets, int64_t n_haystacks) {
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= n_haystacks; h += (int64_t)gridDim.x * blockDim.x) match_offsets[h] = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) unit_offsets[0] = 0;
 }
 
 }  // namespace acb
@@ -177,7 +245,7 @@ struct acb_automaton {
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;
-static acb_tuning g_tuning = {0, 0, 0};
+static acb_tuning g_tuning = {0, 0, 0, 0};
 
 // optional device timing of the dominant (scan) kernel, for bench.py's roofline
 static bool g_timing = false;
@@ -197,7 +265,7 @@ static int fail(int code, const std::string &msg) {
 extern "C" {
 
 const char *acb_last_error(void) { return g_err.c_str(); }
-const char *acb_version(void) { return "acb200 0.1 (sm_100a)"; }
+const char *acb_version(void) { return "acb200 0.2 (sm_100a)"; }
 uint64_t acb_launch_count(void) { return g_launches; }
 
 int acb_timing_enable(int on) {
@@ -277,15 +345,36 @@ uint32_t acb_hot_rows(const void *host_hot) {
     return (h && h->magic == kHotMagic) ? h->n_rows : 0;
 }
 
-uint64_t acb_scratch_words(uint64_t n_units) {
-    const uint64_t tiles = (n_units + kScanTile - 1) / kScanTile;
-    // [0] task counter | tile sums | chunk code point counts (u32, n_units) | chunk code point offsets (n_units + 1)
-    return 2 + tiles + 1 + (n_units + 1) / 2 + 1 + n_units + 1;
-}
-
-uint64_t acb_chunk_count(uint64_t len, uint32_t chunk_bytes) {
-    if (!chunk_bytes) return 0;
-    return (len + chunk_bytes - 1) / chunk_bytes;
+int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_bytes, uint64_t n_haystacks, acb_plan *plan) {
+    if (!a || !plan) return fail(ACB_EINVAL, "null argument");
+    const uint32_t L = a->impl->hdr.max_pat_len;
+    // the warm-up must cover a whole longest pattern so that the guessed state equals the true one
+    // whenever the true scanner did not restart inside it
+    uint32_t warm = (L + 15u) & ~15u;
+    if (warm < 16) warm = 16;
+    uint32_t seg = g_tuning.segment_bytes > 0 ? (uint32_t)g_tuning.segment_bytes : 1024u;
+    if (seg < 8 * warm) seg = 8 * warm;
+    seg = (seg + 63u) & ~63u;
+    const uint64_t mis = reinterpret_cast<uintptr_t>(dev_bytes) & 63u;  // segment 0 starts at the 64-byte aligned address before the buffer
+    plan->segment_bytes = seg;
+    plan->warm_bytes = warm;
+    plan->n_segments = (total_bytes + mis + seg - 1) / seg;
+    uint64_t stride = 1;
+    if (n_haystacks > 1) {
+        const uint64_t avg = total_bytes / n_haystacks;
+        stride = (avg + seg / 2) / seg;
+        if (stride < 1) stride = 1;
+        if (stride > 65536) stride = 65536;
+    }
+    plan->lane_stride = (uint32_t)stride;
+    plan->reserved = 0;
+    const uint64_t seg_units = 2 * plan->n_segments;
+    plan->n_units = seg_units > n_haystacks ? seg_units : n_haystacks;
+    if (plan->n_units < 1) plan->n_units = 1;
+    const uint64_t tiles = (plan->n_units + kScanTile - 1) / kScanTile;
+    // [0] task counter | unit tile sums | cont tile sums | cont_cum (n_segments + 1)
+    plan->scratch_words = 2 + (tiles + 1) + (tiles + 1) + plan->n_segments + 2;
+    return ACB_OK;
 }
 
 }  // extern "C"
@@ -327,23 +416,41 @@ DevImage make_view(const ImageHeader &h, const void *dev_image) {
     return im;
 }
 
+// dev_hot points at a device copy of a hot image; hot_rows is its row count (the
+// host knows it: acb_hot_rows on the host copy), because the header lives on the device
+int make_hot_view(const acb_automaton *a, const void *dev_hot, uint32_t hot_rows, DevHot &v) {
+    const ImageHeader &ih = a->impl->hdr;
+    if (hot_rows < 1 || (uint64_t)hot_rows * ih.n_cols * 2 > 65535) return fail(ACB_EINVAL, "bad hot image row count");
+    auto align16 = [](uint64_t x) { return (x + 15) & ~uint64_t(15); };
+    const uint8_t *b = static_cast<const uint8_t *>(dev_hot);
+    uint64_t off = align16(sizeof(HotHeader));
+    v.table = reinterpret_cast<const uint16_t *>(b + off);
+    off = align16(off + uint64_t(hot_rows + 1) * ih.n_cols * 2);
+    v.hot2full = reinterpret_cast<const uint32_t *>(b + off);
+    off = align16(off + uint64_t(hot_rows + 1) * 4);
+    v.full2hot = reinterpret_cast<const uint16_t *>(b + off);
+    v.n_rows = hot_rows;
+    return ACB_OK;
+}
+
 template <int MODE, bool CP>
-int launch_plain(const DevImage &im, const Units &U, const Sink &out, const DeviceInfo &d, cudaStream_t st) {
+int launch_plain(const DevImage &im, const Batch &B, const Sink &out, const DeviceInfo &d, cudaStream_t st) {
     const int threads = 128;
-    int64_t blocks = (U.n_units + threads - 1) / threads;
+    int64_t blocks = (B.n_haystacks + threads - 1) / threads;
     const int64_t cap = (int64_t)d.sms * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    scan_plain_kernel<MODE, CP><<<(unsigned)blocks, threads, 0, st>>>(im, U, out);
+    scan_plain_kernel<MODE, CP><<<(unsigned)blocks, threads, 0, st>>>(im, B, out);
     g_launches++;
     return ACB_OK;
 }
 
 template <int MODE, bool CP, int COLMODE>
-int launch_staged(const DevImage &im, const DevHot &hot, const Units &U, const Sink &out, const DeviceInfo &d,
-                  unsigned int *task_counter, cudaStream_t st) {
+int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const SegPlan &P, const Sink &out, SegInfo *seg_info,
+                  const DeviceInfo &d, unsigned int *task_counter, unsigned long long *trap_stats, cudaStream_t st) {
     auto kern = scan_staged_kernel<MODE, CP, COLMODE>;
-    const int64_t tasks = (U.n_units + 31) / 32;
+    const uint64_t q = P.lane_stride;
+    const uint64_t tasks = ((uint64_t)P.n_segments + 32 * q - 1) / (32 * q) * q;
     const int ctas = d.sms;
     int warps = (int)((tasks + ctas - 1) / ctas);
     if (warps < 4) warps = 4;
@@ -359,109 +466,37 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Units &U, const S
     if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
     const uint32_t hot_bytes = (((H + 1) * row_bytes) + 127u) & ~127u;
     const uint32_t smem = hot_bytes + kStageOffset + stage_bytes;
-    static thread_local int configured_for = -1;
-    (void)configured_for;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    CUDA_OK(cudaMemsetAsync(task_counter, 0, sizeof(unsigned int), st));
-    kern<<<ctas, warps * 32, smem, st>>>(im, hot, U, out, H, hot_bytes, task_counter, out.total + 2);
+    kern<<<ctas, warps * 32, smem, st>>>(im, hot, B, P, out, seg_info, H, hot_bytes, task_counter, trap_stats);
     g_launches++;
     return ACB_OK;
 }
 
 template <int MODE, bool CP>
-int launch_scan(const ImageHeader &h, const DevImage &im, const DevHot *hot, const Units &U, const Sink &out,
-                const DeviceInfo &d, unsigned int *task_counter, cudaStream_t st) {
-    int kernel = g_tuning.kernel;
-    if (kernel == 0) kernel = 2;
-    if (!hot) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
-    if (kernel == 1) return launch_plain<MODE, CP>(im, U, out, d, st);
-    if (h.col_mode == kColRange) return launch_staged<MODE, CP, kColRange>(im, *hot, U, out, d, task_counter, st);
-    return launch_staged<MODE, CP, kColClass>(im, *hot, U, out, d, task_counter, st);
+int launch_staged_cols(const ImageHeader &h, const DevImage &im, const DevHot &hot, const Batch &B, const SegPlan &P, const Sink &out,
+                       SegInfo *seg_info, const DeviceInfo &d, unsigned int *task_counter, unsigned long long *trap_stats,
+                       cudaStream_t st) {
+    if (h.col_mode == kColRange)
+        return launch_staged<MODE, CP, kColRange>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
+    return launch_staged<MODE, CP, kColClass>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
 }
 
-// dev_hot points at a device copy of a hot image; hot_rows is its row count (the
-// host knows it: acb_hot_rows on the host copy), because the header lives on the device
-int make_hot_view(const acb_automaton *a, const void *dev_hot, uint32_t hot_rows, DevHot &v) {
-    const ImageHeader &ih = a->impl->hdr;
-    if (hot_rows < 1 || hot_rows > 65534) return fail(ACB_EINVAL, "bad hot image row count");
-    auto align16 = [](uint64_t x) { return (x + 15) & ~uint64_t(15); };
-    const uint8_t *b = static_cast<const uint8_t *>(dev_hot);
-    uint64_t off = align16(sizeof(HotHeader));
-    v.table = reinterpret_cast<const uint16_t *>(b + off);
-    off = align16(off + uint64_t(hot_rows + 1) * ih.n_cols * 2);
-    v.hot2full = reinterpret_cast<const uint32_t *>(b + off);
-    off = align16(off + uint64_t(hot_rows + 1) * 4);
-    v.full2hot = reinterpret_cast<const uint16_t *>(b + off);
-    v.n_rows = hot_rows;
-    return ACB_OK;
-}
-
-int run_scan(const acb_automaton *a, const void *dev_image, const DevHot *hot, const Units &U, int mode, int codepoints,
-             const acb_workspace *ws, cudaStream_t st) {
-    DeviceInfo d;
-    int rc = device_info(d);
-    if (rc) return rc;
-    const ImageHeader &h = a->impl->hdr;
-    const DevImage im = make_view(h, dev_image);
-    Sink out;
-    out.raw = ws->dev_raw;
-    out.raw_seq = ws->dev_raw_seq;
-    out.raw_unit = ws->dev_raw_unit;
-    out.cap = ws->raw_capacity;
-    out.unit_counts = ws->dev_unit_counts;
-    out.total = reinterpret_cast<unsigned long long *>(ws->dev_total);
-    unsigned int *task_counter = reinterpret_cast<unsigned int *>(ws->dev_scratch);
-    unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
-
-    CUDA_OK(cudaMemsetAsync(ws->dev_total, 0, 4 * sizeof(uint64_t), st));
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    if (g_timing && U.n_units > 0) {
-        CUDA_OK(cudaEventCreate(&ev0));
-        CUDA_OK(cudaEventCreate(&ev1));
-    }
-    if (U.n_units > 0) {
-        const bool cp = codepoints != 0;
-        if (ev0) CUDA_OK(cudaEventRecord(ev0, st));
-        if (mode == kModeStandard)
-            rc = cp ? launch_scan<kModeStandard, true>(h, im, hot, U, out, d, task_counter, st)
-                    : launch_scan<kModeStandard, false>(h, im, hot, U, out, d, task_counter, st);
-        else if (mode == kModeLeftmost)
-            rc = cp ? launch_scan<kModeLeftmost, true>(h, im, hot, U, out, d, task_counter, st)
-                    : launch_scan<kModeLeftmost, false>(h, im, hot, U, out, d, task_counter, st);
-        else
-            rc = cp ? launch_scan<kModeOverlap, true>(h, im, hot, U, out, d, task_counter, st)
-                    : launch_scan<kModeOverlap, false>(h, im, hot, U, out, d, task_counter, st);
-        if (rc) return rc;
-        CUDA_OK(cudaGetLastError());
-        if (ev1) {
-            CUDA_OK(cudaEventRecord(ev1, st));
-            g_timing_events.emplace_back(ev0, ev1);
-        }
-    }
-    // counts -> offsets -> ordered output
-    const uint64_t n = (uint64_t)U.n_units;
-    const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
-    if (n == 0) {
-        CUDA_OK(cudaMemsetAsync(ws->dev_unit_offsets, 0, sizeof(uint64_t), st));
-    } else {
-        scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(ws->dev_unit_counts, n, tile_sums);
-        scan_tile_offsets<<<1, kScanThreads, 0, st>>>(tile_sums, tiles);
-        scan_apply<<<(unsigned)tiles, kScanThreads, 0, st>>>(ws->dev_unit_counts, n, tile_sums,
-                                                             reinterpret_cast<unsigned long long *>(ws->dev_unit_offsets));
-        order_matches_kernel<<<d.sms * 4, 256, 0, st>>>(ws->dev_raw, ws->dev_raw_seq, ws->dev_raw_unit, ws->raw_capacity,
-                                                       out.total, reinterpret_cast<unsigned long long *>(ws->dev_unit_offsets),
-                                                       ws->dev_out, ws->out_capacity);
-        g_launches += 4;
-    }
-    finish_total_kernel<<<1, 1, 0, st>>>(out.total, ws->raw_capacity, ws->out_capacity);
+template <int MODE, bool CP>
+int launch_repair(const DevImage &im, const Batch &B, const SegPlan &P, const Sink &out, SegInfo *seg_info,
+                  unsigned long long *stats, const DeviceInfo &d, cudaStream_t st) {
+    int64_t blocks = (B.n_haystacks + 127) / 128;
+    const int64_t cap = (int64_t)d.sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    repair_kernel<MODE, CP><<<(unsigned)blocks, 128, 0, st>>>(im, B, P, out, seg_info, stats);
     g_launches++;
-    CUDA_OK(cudaGetLastError());
     return ACB_OK;
 }
 
 int check_ws(const acb_workspace *ws) {
-    if (!ws || !ws->dev_raw || !ws->dev_raw_seq || !ws->dev_raw_unit || !ws->dev_unit_counts || !ws->dev_unit_offsets ||
-        !ws->dev_scratch || !ws->dev_total || !ws->dev_out)
+    if (!ws || !ws->dev_raw || !ws->dev_raw_seq || !ws->dev_raw_unit || !ws->dev_raw_aux || !ws->dev_unit_counts ||
+        !ws->dev_unit_offsets || !ws->dev_seg_info || !ws->dev_scratch || !ws->dev_total || !ws->dev_out ||
+        !ws->dev_match_offsets)
         return fail(ACB_EINVAL, "workspace has a null buffer");
     return ACB_OK;
 }
@@ -471,96 +506,165 @@ int check_ws(const acb_workspace *ws) {
 extern "C" {
 
 int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, const int64_t *dev_offsets,
-                int64_t n_haystacks, uint64_t len, int overlapping, uint32_t *dev_visits, void *stream) {
-    if (!a || !dev_image || !dev_visits) return fail(ACB_EINVAL, "bad argument");
+                int64_t n_haystacks, uint64_t total_bytes, int overlapping, uint32_t *dev_visits, void *stream) {
+    if (!a || !dev_image || !dev_visits || !dev_offsets) return fail(ACB_EINVAL, "bad argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const ImageHeader &h = a->impl->hdr;
     CUDA_OK(cudaMemsetAsync(dev_visits, 0, uint64_t(h.n_states) * 4, st));
-    Units U{};
-    U.bytes = dev_bytes;
-    U.offsets = dev_offsets;
-    U.n_units = n_haystacks;
-    U.len = len;
-    U.chunk = dev_offsets ? 0 : 1;
+    if (n_haystacks < 1 || total_bytes == 0) return ACB_OK;
+    Batch B{dev_bytes, dev_offsets, n_haystacks};
     int64_t n_samples = 256;
-    if (dev_offsets) {
-        if (n_haystacks < 1) return ACB_OK;
-        if (n_samples > n_haystacks) n_samples = n_haystacks;
-    } else {
-        if (len == 0) return ACB_OK;
-        if ((uint64_t)n_samples > len / 1024 + 1) n_samples = (int64_t)(len / 1024 + 1);
-    }
+    if ((uint64_t)n_samples > total_bytes / 1024 + 1) n_samples = (int64_t)(total_bytes / 1024 + 1);
     const DevImage im = make_view(h, dev_image);
     const int restart = (!overlapping && h.match_kind == ACB_STANDARD) ? 1 : 0;
-    profile_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, st>>>(im, U, dev_visits, n_samples, 1024, restart);
+    profile_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, st>>>(im, B, dev_visits, n_samples, 1024, restart);
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return ACB_OK;
 }
 
 int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
-                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, int overlapping,
-                   int codepoints, const acb_workspace *ws, void *stream) {
-    if (!a || !dev_image || !dev_offsets || n_haystacks < 0) return fail(ACB_EINVAL, "bad argument");
-    if (n_haystacks > 0xffffffffll) return fail(ACB_EINVAL, "too many haystacks in one batch");
-    const int kind = (int)a->impl->hdr.match_kind;
+                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
+                   int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream) {
+    if (!a || !dev_image || !dev_offsets || n_haystacks < 0 || !plan) return fail(ACB_EINVAL, "bad argument");
+    if (n_haystacks > 0xfffffffell) return fail(ACB_EINVAL, "too many haystacks in one batch");
+    const ImageHeader &h = a->impl->hdr;
+    const int kind = (int)h.match_kind;
     if (overlapping && kind != ACB_STANDARD)
         return fail(ACB_EUNSUPPORTED, std::string("match kind ") + (kind == ACB_LEFTMOST_FIRST ? "LeftmostFirst" : "LeftmostLongest") +
                                           " does not support overlapping searches");
     int rc = check_ws(ws);
     if (rc) return rc;
-    Units U{};
-    U.bytes = dev_bytes;
-    U.offsets = dev_offsets;
-    U.n_units = n_haystacks;
-    U.chunk = 0;
-    const int mode = overlapping ? kModeOverlap : (kind == ACB_STANDARD ? kModeStandard : kModeLeftmost);
-    DevHot hot;
-    if (dev_hot && (rc = make_hot_view(a, dev_hot, hot_rows, hot))) return rc;
-    return run_scan(a, dev_image, dev_hot ? &hot : nullptr, U, mode, codepoints, ws, static_cast<cudaStream_t>(stream));
-}
-
-int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
-                     const uint8_t *dev_bytes, uint64_t len, uint32_t chunk_bytes, int codepoints,
-                     const acb_workspace *ws, void *stream) {
-    if (!a || !dev_image || (!dev_bytes && len)) return fail(ACB_EINVAL, "bad argument");
-    if (chunk_bytes < 64) return fail(ACB_EINVAL, "chunk_bytes must be at least 64");
-    if (len >= 0xffffffffull) return fail(ACB_EINVAL, "haystacks of 4 GiB and more are not supported yet");
-    const int kind = (int)a->impl->hdr.match_kind;
-    if (kind != ACB_STANDARD)
-        return fail(ACB_EUNSUPPORTED, std::string("match kind ") + (kind == ACB_LEFTMOST_FIRST ? "LeftmostFirst" : "LeftmostLongest") +
-                                          " does not support overlapping searches");
-    int rc = check_ws(ws);
-    if (rc) return rc;
+    DeviceInfo d;
+    if ((rc = device_info(d))) return rc;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    Units U{};
-    U.bytes = dev_bytes;
-    U.offsets = nullptr;
-    U.n_units = (int64_t)acb_chunk_count(len, chunk_bytes);
-    U.len = len;
-    U.chunk = chunk_bytes;
-    const uint32_t L = a->impl->hdr.max_pat_len;
-    U.halo = L ? L - 1 : 0;
-    U.chunk_cp = nullptr;
-    if (codepoints && U.n_units) {
-        // code points before each chunk: count per chunk, then prefix-sum
-        const uint64_t n = (uint64_t)U.n_units;
-        const uint64_t tiles = (n + kScanTile - 1) / kScanTile;
-        unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
-        uint32_t *cnt = reinterpret_cast<uint32_t *>(tile_sums + tiles + 1);
-        unsigned long long *offs = tile_sums + tiles + 1 + (n + 1) / 2 + 1;
-        const unsigned blocks = (unsigned)((n * 32 + 255) / 256);
-        chunk_cp_count_kernel<<<blocks, 256, 0, st>>>(dev_bytes, len, chunk_bytes, cnt, n);
-        scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(cnt, n, tile_sums);
-        scan_tile_offsets<<<1, kScanThreads, 0, st>>>(tile_sums, tiles);
-        scan_apply<<<(unsigned)tiles, kScanThreads, 0, st>>>(cnt, n, tile_sums, offs);
-        g_launches += 4;
+    const int mode = overlapping ? kModeOverlap : (kind == ACB_STANDARD ? kModeStandard : kModeLeftmost);
+    const bool cp = codepoints != 0;
+    const DevImage im = make_view(h, dev_image);
+    Batch B{dev_bytes, dev_offsets, n_haystacks};
+
+    // the plan must be the one acb_plan_scan gives for these arguments (it sizes the workspace)
+    acb_plan want;
+    acb_plan_scan(a, dev_bytes, total_bytes, (uint64_t)n_haystacks, &want);
+    if (want.n_segments != plan->n_segments || want.segment_bytes != plan->segment_bytes || want.n_units != plan->n_units)
+        return fail(ACB_EINVAL, "plan does not match the arguments (call acb_plan_scan again)");
+
+    unsigned long long *totals = reinterpret_cast<unsigned long long *>(ws->dev_total);
+    unsigned int *task_counter = reinterpret_cast<unsigned int *>(ws->dev_scratch);
+    Sink out;
+    out.raw = ws->dev_raw;
+    out.raw_seq = ws->dev_raw_seq;
+    out.raw_unit = ws->dev_raw_unit;
+    out.raw_aux = ws->dev_raw_aux;
+    out.cap = ws->raw_capacity;
+    out.unit_counts = ws->dev_unit_counts;
+    out.raw_total = totals + 4;
+    SegInfo *seg_info = reinterpret_cast<SegInfo *>(ws->dev_seg_info);
+
+    clear_totals_kernel<<<1, 32, 0, st>>>(totals, task_counter);
+    g_launches++;
+    unsigned long long *unit_offsets = reinterpret_cast<unsigned long long *>(ws->dev_unit_offsets);
+    unsigned long long *match_offsets = reinterpret_cast<unsigned long long *>(ws->dev_match_offsets);
+    if (n_haystacks == 0 || total_bytes == 0) {
+        zero_outputs_kernel<<<(unsigned)((n_haystacks + 256) / 256), 256, 0, st>>>(unit_offsets, match_offsets, n_haystacks);
+        g_launches++;
         CUDA_OK(cudaGetLastError());
-        U.chunk_cp = reinterpret_cast<const uint64_t *>(offs);
+        return ACB_OK;
     }
-    DevHot hot;
-    if (dev_hot && (rc = make_hot_view(a, dev_hot, hot_rows, hot))) return rc;
-    return run_scan(a, dev_image, dev_hot ? &hot : nullptr, U, kModeOverlap, codepoints, ws, st);
+
+    int kernel = g_tuning.kernel;
+    if (kernel == 0) kernel = 2;
+    if (!dev_hot) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
+    const bool segments = kernel == 2;
+    SegPlan P{};
+    uint64_t n_units = (uint64_t)n_haystacks;
+
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (g_timing) {
+        CUDA_OK(cudaEventCreate(&ev0));
+        CUDA_OK(cudaEventCreate(&ev1));
+        CUDA_OK(cudaEventRecord(ev0, st));
+    }
+#define ACB_DISPATCH(FN, ...)                                                                                      \
+    (mode == kModeStandard   ? (cp ? FN<kModeStandard, true>(__VA_ARGS__) : FN<kModeStandard, false>(__VA_ARGS__)) \
+     : mode == kModeLeftmost ? (cp ? FN<kModeLeftmost, true>(__VA_ARGS__) : FN<kModeLeftmost, false>(__VA_ARGS__)) \
+                             : (cp ? FN<kModeOverlap, true>(__VA_ARGS__) : FN<kModeOverlap, false>(__VA_ARGS__)))
+    if (segments) {
+        DevHot hot;
+        if ((rc = make_hot_view(a, dev_hot, hot_rows, hot))) return rc;
+        // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
+        // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
+        P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);
+        P.seg_bytes = plan->segment_bytes;
+        P.warm = plan->warm_bytes;
+        P.n_segments = (int64_t)plan->n_segments;
+        P.lane_stride = plan->lane_stride;
+        n_units = 2 * plan->n_segments;
+        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st);
+        if (rc) return rc;
+        CUDA_OK(cudaGetLastError());
+        if (ev1) {
+            CUDA_OK(cudaEventRecord(ev1, st));
+            g_timing_events.emplace_back(ev0, ev1);
+        }
+        if (mode != kModeOverlap) {
+            rc = ACB_DISPATCH(launch_repair, im, B, P, out, seg_info, totals + 5, d, st);
+            if (rc) return rc;
+            CUDA_OK(cudaGetLastError());
+        }
+    } else {
+        rc = ACB_DISPATCH(launch_plain, im, B, out, d, st);
+        if (rc) return rc;
+        CUDA_OK(cudaGetLastError());
+        if (ev1) {
+            CUDA_OK(cudaEventRecord(ev1, st));
+            g_timing_events.emplace_back(ev0, ev1);
+        }
+    }
+#undef ACB_DISPATCH
+
+    // counts -> offsets -> ordered output -> per-haystack offsets
+    const uint64_t tiles = (n_units + kScanTile - 1) / kScanTile;
+    unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
+    scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(ws->dev_unit_counts, 1, n_units, tile_sums);
+    scan_tile_offsets<<<1, kScanThreads, 0, st>>>(tile_sums, tiles);
+    scan_apply<<<(unsigned)tiles, kScanThreads, 0, st>>>(ws->dev_unit_counts, 1, n_units, tile_sums, unit_offsets);
+    g_launches += 3;
+    const uint64_t max_tiles = (plan->n_units + kScanTile - 1) / kScanTile;
+    unsigned long long *cont_tiles = tile_sums + max_tiles + 1;
+    unsigned long long *cont_cum = cont_tiles + max_tiles + 1;
+    if (segments && cp) {
+        // exclusive prefix sum of SegInfo.cont_tail (8 u32 per segment, field 5)
+        const uint64_t ns = plan->n_segments, t2 = (ns + kScanTile - 1) / kScanTile;
+        const uint32_t *ct = reinterpret_cast<const uint32_t *>(seg_info) + 5;
+        scan_tile_sums<<<(unsigned)t2, kScanThreads, 0, st>>>(ct, 8, ns, cont_tiles);
+        scan_tile_offsets<<<1, kScanThreads, 0, st>>>(cont_tiles, t2);
+        scan_apply<<<(unsigned)t2, kScanThreads, 0, st>>>(ct, 8, ns, cont_tiles, cont_cum);
+        g_launches += 3;
+    }
+    OrderArgs A;
+    A.raw = ws->dev_raw;
+    A.raw_seq = ws->dev_raw_seq;
+    A.raw_unit = ws->dev_raw_unit;
+    A.raw_aux = ws->dev_raw_aux;
+    A.raw_cap = ws->raw_capacity;
+    A.raw_total = totals + 4;
+    A.unit_offsets = unit_offsets;
+    A.seg_info = segments ? seg_info : nullptr;
+    A.cont_cum = cont_cum;
+    A.hay_offsets = dev_offsets;
+    A.pat_cplen = im.pat_cplen;
+    A.origin = P.origin;
+    A.seg_bytes = P.seg_bytes;
+    A.codepoints = cp ? 1 : 0;
+    A.out = ws->dev_out;
+    A.out_cap = ws->out_capacity;
+    order_matches_kernel<<<d.sms * 4, 256, 0, st>>>(A);
+    match_offsets_kernel<<<d.sms * 2, 256, 0, st>>>(ws->dev_out, unit_offsets, n_units, totals, ws->raw_capacity, ws->out_capacity,
+                                                    n_haystacks, match_offsets);
+    g_launches += 2;
+    CUDA_OK(cudaGetLastError());
+    return ACB_OK;
 }
 
 }  // extern "C"

@@ -2,11 +2,13 @@
 //
 // The exact (byte-at-a-time) scanner below is the definition of the result:
 // it is the reference's iterator drain (src/lib.rs:42-68, 238-248, 433; the
-// crate's find / find_overlapping loops) run by ONE thread over ONE scan unit,
-// reading the dense table in global memory.  The staged kernel (scan_staged.cuh)
-// only accelerates the stretches where nothing can happen and drops back here
-// for everything else, so both kernels produce the same matches in the same
-// order by construction.
+// crate's find / find_overlapping loops) run by ONE thread, reading the dense
+// table in global memory.  The staged kernel (scan_staged.cuh) only
+// accelerates the stretches where nothing can happen and drops back here for
+// everything else, and the segment-parallel scheme (DESIGN.md "Segments")
+// validates every speculative start against the true state and repairs the
+// rare misses with this same scanner, so all kernels produce the same matches
+// in the same order by construction.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -22,6 +24,9 @@ enum ScanMode : int {
     kModeOverlap = 2,   // every pattern on every match state's list, never restart
 };
 
+constexpr uint32_t kNoState = 0xffffffffu;    // SegInfo.spec_state: the segment starts at a haystack start
+constexpr uint32_t kSpecSkipped = 0xfffffffeu;  // SegInfo.spec_state: no usable speculation, head piece left to the repair pass
+
 // Views into the device image (all global memory).
 struct DevImage {
     const uint8_t *colmap;
@@ -33,71 +38,97 @@ struct DevImage {
     uint32_t n_cols, col_lo, n_states, col_mode;
 };
 
-// What to scan.  Batch: unit u = haystack u = bytes[offsets[u], offsets[u+1]).
-// Chunked: one haystack of `len` bytes, unit u emits matches that END in
-// (u*chunk, (u+1)*chunk] and starts reading `halo` bytes earlier.
-struct Units {
+// The input: haystack h = bytes[offsets[h], offsets[h+1]).
+struct Batch {
     const uint8_t *bytes;
-    const int64_t *offsets;  // batch only
-    int64_t n_units;
-    uint64_t len;            // chunked only
-    uint32_t chunk, halo;    // chunk == 0 => batch
-    const uint64_t *chunk_cp;  // chunked + codepoints: code points before each chunk
+    const int64_t *offsets;
+    int64_t n_haystacks;
+};
+
+// Segments: the byte stream [offsets[0], offsets[n]) cut on a fixed grid of
+// `seg_bytes` (a multiple of 64, anchored at a 64-byte aligned ADDRESS), so
+// every lane gets the same amount of work whatever the haystack lengths are.
+// A segment that starts in the middle of a haystack starts from a SPECULATED
+// state (obtained by scanning `warm` bytes before it from the root); the
+// validate/repair pass checks it against the true state.
+struct SegPlan {
+    int64_t origin;       // stream position of segment 0's grid start: the 64-byte aligned address at or before `bytes`
+    uint32_t seg_bytes;   // (the stream itself is [offsets[0], offsets[n]), read on the device)
+    uint32_t warm;        // multiple of 16, >= max_pattern_len - 1
+    int64_t n_segments;
+    uint32_t lane_stride;  // lane l of warp-task (a, j) scans segment (32 a + l) * lane_stride + j
+};
+
+// Per-segment summary written by the scan kernel, read by validate/repair and the ordering pass.
+struct SegInfo {
+    uint32_t spec_state;  // state assumed at the segment start (kNoState / kSpecSkipped: see above)
+    uint32_t end_state;   // state when the scan stopped (meaningful when the segment ends inside a haystack)
+    uint32_t end_over;    // how far past the segment end the scan stopped (leftmost kinds may overrun)
+    uint32_t head_count;  // matches reported by the speculative head piece (the first head_count of slot 1)
+    uint32_t drop;        // leading slot-1 matches superseded by the repair pass
+    uint32_t cont_tail;   // code points: continuation bytes of the last piece (the one that runs into the next segment)
+    uint32_t reserved0, reserved1;
 };
 
 struct Sink {
     acb_match *raw;
     uint32_t *raw_seq;
     uint32_t *raw_unit;
+    uint32_t *raw_aux;  // code points: continuation bytes between the piece's counting origin and the match end
     unsigned long long cap;
     uint32_t *unit_counts;
-    unsigned long long *total;
+    unsigned long long *raw_total;
 };
 
-// Per-unit scanner state.  Positions are relative to `base` (the haystack's
-// first byte), so they fit 32 bits for haystacks below 4 GiB.
-struct UnitCtx {
+// Scanner state for one piece (the part of one haystack inside one scan unit).
+// Positions are relative to `base`; position + hay_delta = byte offset in the haystack.
+struct PieceCtx {
     const uint8_t *base;
     uint32_t at;         // next byte to read
-    uint32_t end;        // one past the last byte of the unit
-    uint32_t emit_from;  // report only matches with end > emit_from (halo suppression)
+    uint32_t stop;       // end of this piece (the scan runs past it only while a leftmost match is pending)
+    uint32_t limit;      // end of the haystack = end of input
+    uint32_t emit_from;  // report only matches that end after this position
     uint32_t state;
-    uint32_t nemit;      // matches reported so far = rank of the next one inside the unit
-    uint32_t unit, hay;
-    // leftmost: the match that will be reported once the automaton dies / input ends
-    uint32_t have, last_pid, last_end;
-    // code points: number of non-continuation bytes in [base, cp_pos)
-    uint32_t cp_pos, cp_count;
+    uint32_t have, last_pid, last_end;  // leftmost: the match to report once the automaton dies / input ends
+    uint32_t hay, hay_delta;
+    uint32_t unit, nemit;      // output slot and rank of the next match in it
+    uint32_t cp_pos, cp_cont;  // code points: continuation bytes counted in [counting origin, cp_pos)
 };
 
 __device__ __forceinline__ uint32_t ld_u8(const uint8_t *p) { return __ldg(p); }
 
+// advance the continuation-byte counter to position `to` (no-op when already there or past it)
+__device__ __forceinline__ void cp_catch_up(PieceCtx &c, uint32_t to) {
+    uint32_t p = c.cp_pos, n = c.cp_cont;
+    while (p < to) {
+        n += (ld_u8(c.base + p) & 0xC0u) == 0x80u;
+        p++;
+    }
+    c.cp_pos = p;
+    c.cp_cont = n;
+}
+
 template <bool CP>
-__device__ __forceinline__ void report(UnitCtx &c, const DevImage &im, const Sink &out, uint32_t pid, uint32_t end) {
+__device__ __forceinline__ void report(PieceCtx &c, const DevImage &im, const Sink &out, uint32_t pid, uint32_t end) {
     if (end <= c.emit_from) return;
-    uint32_t start = end - __ldg(im.pat_len + pid);
+    uint32_t aux = 0;
     if (CP) {
         // ends are reported in non-decreasing order, so one forward-only counter is enough
-        uint32_t pos = c.cp_pos, cnt = c.cp_count;
-        while (pos < end) {
-            cnt += (ld_u8(c.base + pos) & 0xC0u) != 0x80u;
-            pos++;
-        }
-        c.cp_pos = pos;
-        c.cp_count = cnt;
-        end = cnt;
-        start = cnt - __ldg(im.pat_cplen + pid);
+        cp_catch_up(c, end);
+        aux = c.cp_cont;
     }
-    unsigned long long i = atomicAdd(out.total, 1ULL);
+    const uint32_t hend = end + c.hay_delta;
+    const unsigned long long i = atomicAdd(out.raw_total, 1ULL);
     if (i < out.cap) {
         acb_match m;
         m.haystack = c.hay;
         m.pattern = pid;
-        m.start = start;
-        m.end = end;
+        m.start = hend - __ldg(im.pat_len + pid);
+        m.end = hend;
         *reinterpret_cast<uint4 *>(out.raw + i) = *reinterpret_cast<uint4 *>(&m);
         out.raw_seq[i] = c.nemit;
         out.raw_unit[i] = c.unit;
+        if (CP) out.raw_aux[i] = aux;
     }
     c.nemit++;
 }
@@ -108,96 +139,82 @@ struct HotMap {
     uint32_t hot_limit;
 };
 
-// Runs the exact scanner from c.at.  It returns when the unit is finished
-// (c.at == c.end with nothing pending), or -- if stop_hot is set -- as soon as
+// One transition and its consequences.  Shared by exact_scan and the repair
+// pass (which steps two scanners side by side), so both follow the same rules.
+template <int MODE, typename Emit>
+__device__ __forceinline__ void scan_byte(PieceCtx &c, const DevImage &im, uint32_t &s, uint32_t &at, Emit &&emit) {
+    const uint32_t col = __ldg(im.colmap + ld_u8(c.base + at));
+    const uint32_t e = __ldg(im.trans + (size_t)s * im.n_cols + col);
+    s = e & kStateMask;
+    at++;
+    if (e & kMatchFlag) {
+        const uint32_t m0 = __ldg(im.match_off + s);
+        if (MODE == kModeStandard) {
+            emit(__ldg(im.match_pid + m0), at);
+            s = kRoot;
+        } else if (MODE == kModeLeftmost) {
+            c.have = 1;
+            c.last_pid = __ldg(im.match_pid + m0);
+            c.last_end = at;
+        } else {
+            const uint32_t m1 = __ldg(im.match_off + s + 1);
+            for (uint32_t k = m0; k < m1; k++) emit(__ldg(im.match_pid + k), at);
+        }
+    }
+}
+
+// Leftmost kinds: what happens BEFORE reading the next byte.  Returns true when
+// a pending match was reported and the search restarted right behind it.
+template <int MODE, typename Emit>
+__device__ __forceinline__ bool leftmost_flush(PieceCtx &c, uint32_t &s, uint32_t &at, Emit &&emit) {
+    if (MODE != kModeLeftmost) return false;
+    if (s == kDead || at == c.limit) {
+        if (c.have) {
+            // the crate's iterator: report, then search again from the match end
+            emit(c.last_pid, c.last_end);
+            at = c.last_end;
+            c.have = 0;
+            s = kRoot;
+            return true;
+        }
+        if (s == kDead) s = kRoot;  // unreachable: the dead state is only entered below a match state
+    }
+    return false;
+}
+
+// Runs the exact scanner from c.at until the piece is finished: at >= c.stop
+// with nothing pending (leftmost kinds run past c.stop while a match is
+// pending, never past c.limit) -- or, if stop_hot is set, as soon as
 //   at >= min_at, (at - phase) % 16 == 0, the state is hot and nothing is pending,
 // i.e. at a point where the staged fast path may take over again.
 template <int MODE, bool CP>
-__device__ __noinline__ void exact_scan(UnitCtx &c, const DevImage &im, const Sink &out, bool stop_hot,
+__device__ __noinline__ void exact_scan(PieceCtx &c, const DevImage &im, const Sink &out, bool stop_hot,
                                         uint32_t min_at, uint32_t phase, HotMap hm) {
     uint32_t s = c.state, at = c.at;
-    const uint32_t end = c.end;
+    auto emit = [&](uint32_t pid, uint32_t end) { report<CP>(c, im, out, pid, end); };
     for (;;) {
-        if (MODE == kModeLeftmost) {
-            if (at == end || s == kDead) {
-                if (c.have) {
-                    // the crate's iterator: report, then search again from the match end
-                    report<CP>(c, im, out, c.last_pid, c.last_end);
-                    at = c.last_end;
-                    c.have = 0;
-                    s = kRoot;
-                    continue;
-                }
-                if (at == end) break;
-                s = kRoot;  // unreachable: the dead state is only entered below a match state
-            }
-        } else {
-            if (at == end) break;
-        }
+        if (leftmost_flush<MODE>(c, s, at, emit)) continue;
+        if (at >= c.stop && (MODE != kModeLeftmost || !c.have)) break;
         if (stop_hot && at >= min_at && ((at - phase) & 15u) == 0 && (MODE != kModeLeftmost || !c.have) &&
             (uint32_t)__ldg(hm.full2hot + s) < hm.hot_limit)
             break;
-        const uint32_t col = __ldg(im.colmap + ld_u8(c.base + at));
-        const uint32_t e = __ldg(im.trans + (size_t)s * im.n_cols + col);
-        s = e & kStateMask;
-        at++;
-        if (e & kMatchFlag) {
-            const uint32_t m0 = __ldg(im.match_off + s);
-            if (MODE == kModeStandard) {
-                report<CP>(c, im, out, __ldg(im.match_pid + m0), at);
-                s = kRoot;
-            } else if (MODE == kModeLeftmost) {
-                c.have = 1;
-                c.last_pid = __ldg(im.match_pid + m0);
-                c.last_end = at;
-            } else {
-                const uint32_t m1 = __ldg(im.match_off + s + 1);
-                for (uint32_t k = m0; k < m1; k++) report<CP>(c, im, out, __ldg(im.match_pid + k), at);
-            }
-        }
+        scan_byte<MODE>(c, im, s, at, emit);
     }
     c.state = s;
     c.at = at;
 }
 
-// Fills in a unit's context.  Returns false when u is out of range.
-template <bool CP>
-__device__ __forceinline__ bool init_unit(UnitCtx &c, const Units &U, int64_t u) {
-    if (u >= U.n_units) return false;
-    c.unit = (uint32_t)u;
-    c.state = kRoot;
-    c.nemit = 0;
-    c.have = 0;
-    c.last_pid = 0;
-    c.last_end = 0;
-    if (U.chunk == 0) {
-        const int64_t b = U.offsets[u], e = U.offsets[u + 1];
-        c.base = U.bytes + b;
-        c.at = 0;
-        c.end = (uint32_t)(e - b);
-        c.emit_from = 0;
-        c.hay = (uint32_t)u;
-        c.cp_pos = 0;
-        c.cp_count = 0;
-    } else {
-        const uint64_t lo = (uint64_t)u * U.chunk;
-        uint64_t hi = lo + U.chunk;
-        if (hi > U.len) hi = U.len;
-        c.base = U.bytes;
-        c.at = (uint32_t)(lo > U.halo ? lo - U.halo : 0);
-        c.end = (uint32_t)hi;
-        c.emit_from = (uint32_t)lo;
-        c.hay = 0;
-        // code points before the first byte this unit READS (the halo starts before the chunk)
-        c.cp_pos = c.at;
-        c.cp_count = 0;
-        if (CP) {
-            uint32_t n = (uint32_t)U.chunk_cp[u];
-            for (uint32_t p = c.at; p < (uint32_t)lo; p++) n -= (ld_u8(c.base + p) & 0xC0u) != 0x80u;
-            c.cp_count = n;
-        }
+// index of the haystack containing stream position p (offsets[h] <= p < offsets[h+1]); n when p is at/after the end
+__device__ __forceinline__ int64_t find_haystack(const Batch &B, int64_t p) {
+    int64_t lo = 0, hi = B.n_haystacks;  // answer in [lo, hi]
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (__ldg(B.offsets + mid + 1) <= p)
+            lo = mid + 1;
+        else
+            hi = mid;
     }
-    return true;
+    return lo;
 }
 
 }  // namespace acb

@@ -1,5 +1,6 @@
-// scan_staged.cuh -- the hot kernel: one lane per scan unit, hot table rows in
-// shared memory, haystack bytes staged through shared memory with cp.async.
+// scan_staged.cuh -- the hot kernel: one lane per SEGMENT of the byte stream,
+// hot table rows in shared memory, bytes staged through shared memory with
+// cp.async.
 //
 // Layout per CTA (dynamic shared memory):
 //   [ hot table : (H + 1) rows x n_cols u16 ]  rows 0..H-1 are the H hottest
@@ -18,7 +19,19 @@
 //        chunk, 16-byte units XOR-swizzled with (l >> 1) & 3 so the per-lane
 //        LDS.128 reads are bank-conflict free.
 //
-// Each lane walks its own unit in 64-byte chunks of the ABSOLUTE address grid,
+// Work decomposition (scan_core.cuh: SegPlan).  The stream is cut into
+// fixed-size segments; a lane scans one segment, walking through whatever
+// haystack boundaries fall inside it (each haystack start resets the scanner to
+// the root, exactly).  A segment that begins inside a haystack begins with a
+// speculated state: the lane first scans `warm` bytes before the segment from
+// the root, silently, and takes the state it arrives with.  It records that
+// state and its end state in SegInfo; repair.cuh verifies the chain and redoes
+// the few places where the guess was wrong.  Lanes of a warp take segments
+// `lane_stride` apart, which for a batch of equal-length haystacks puts all 32
+// lanes at the same offset of 32 different haystacks (same text -> same table
+// row -> shared-memory broadcasts instead of bank conflicts).
+//
+// Each lane reads its bytes in 64-byte chunks of the ABSOLUTE address grid,
 // so every cp.async is 16-byte aligned and a warp-wide copy instruction
 // touches 8 x 64 contiguous bytes.  Chunk k+1 is in flight while chunk k is
 // scanned (the scan of a chunk takes longer than an HBM round trip).
@@ -54,17 +67,6 @@ __device__ __forceinline__ uint32_t fstep4(uint32_t s, uint32_t w, const FastTab
 
 // continuation bytes (10xxxxxx) in a word
 __device__ __forceinline__ uint32_t cont_bytes(uint32_t w) { return __popc(w & ~(w << 1) & 0x80808080u); }
-
-// advance the code point counter to position `to` (no-op when already there or past it)
-__device__ __forceinline__ void cp_catch_up(UnitCtx &c, uint32_t to) {
-    uint32_t p = c.cp_pos, n = c.cp_count;
-    while (p < to) {
-        n += (ld_u8(c.base + p) & 0xC0u) != 0x80u;
-        p++;
-    }
-    c.cp_pos = p;
-    c.cp_count = n;
-}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, uint32_t src_bytes) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst_smem), "l"(src), "r"(src_bytes) : "memory");
@@ -107,10 +109,126 @@ struct DevHot {
     uint32_t n_rows;
 };
 
+// What a lane knows about its segment besides the scanner state (kept out of
+// the hot loop's registers: only touched at piece boundaries).
+enum PieceKind : uint32_t { kPieceWarm = 0, kPieceHead = 1, kPieceNormal = 2 };
+struct LaneSeg {
+    int64_t org;         // stream position of c.base
+    int64_t seg;         // segment index
+    uint32_t lo_rel, hi_rel;  // the segment, relative to org
+    uint32_t h;          // current haystack
+    uint32_t kind;
+    uint32_t spec_state, head_count;
+    uint32_t done;
+};
+
+// The current piece is finished (c.at >= c.stop, nothing pending): move on.  Either starts the next
+// piece (c.at = its first byte, c.state = its start state) or sets L.done and writes the segment summary.
+template <int MODE, bool CP>
+__device__ __noinline__ void advance_piece(PieceCtx &c, LaneSeg &L, const Batch &B, const Sink &out, SegInfo *seg_info) {
+    bool finish_segment = false;
+    if (L.kind == kPieceWarm) {
+        const uint32_t he_rel = c.limit;
+        const uint32_t piece_end = min(L.hi_rel, he_rel);
+        if (c.at == L.lo_rel) {
+            // arrived at the segment start with a guess for the state there: scan the head piece from it
+            L.spec_state = c.state;
+            L.kind = kPieceHead;
+            c.stop = piece_end;
+            c.emit_from = 0;
+            c.cp_pos = c.at;
+            c.cp_cont = 0;
+            return;
+        }
+        // a leftmost match kept the scanner busy past the segment start: no usable guess.
+        // Leave the whole head piece to the repair pass.
+        L.spec_state = kSpecSkipped;
+        L.kind = kPieceHead;
+        c.at = piece_end;
+        c.stop = piece_end;
+        c.emit_from = 0;
+        c.state = kRoot;
+        c.have = 0;
+        c.cp_pos = L.lo_rel;  // its continuation bytes still have to be counted for the segments after it
+        c.cp_cont = 0;
+        // fall through: the (skipped) head piece is finished
+    }
+    if (L.kind == kPieceHead) L.head_count = c.nemit;
+    if (c.stop == c.limit) {
+        // the piece ended with its haystack: continue with the next non-empty haystack, if it starts inside the segment
+        int64_t h = (int64_t)L.h + 1;
+        while (h < B.n_haystacks && __ldg(B.offsets + h + 1) == __ldg(B.offsets + h)) h++;
+        const int64_t hi_pos = L.org + L.hi_rel;
+        if (h < B.n_haystacks && __ldg(B.offsets + h) < hi_pos) {
+            const int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);
+            L.h = (uint32_t)h;
+            L.kind = kPieceNormal;
+            c.at = (uint32_t)(hs - L.org);
+            c.limit = (uint32_t)(he - L.org);
+            c.stop = min(L.hi_rel, c.limit);
+            c.emit_from = 0;
+            c.state = kRoot;
+            c.have = 0;
+            c.hay = (uint32_t)h;
+            c.hay_delta = (uint32_t)(L.org - hs);
+            c.cp_pos = c.at;
+            c.cp_cont = 0;
+            return;
+        }
+        finish_segment = true;
+    } else {
+        finish_segment = true;  // the segment ends inside this haystack
+    }
+    if (finish_segment) {
+        SegInfo si;
+        si.spec_state = L.spec_state;
+        si.end_state = c.state;
+        si.end_over = c.at - L.hi_rel;
+        si.head_count = L.head_count;
+        si.drop = 0;
+        si.cont_tail = 0;
+        si.reserved0 = si.reserved1 = 0;
+        if (CP) {
+            // continuation bytes of the last piece inside the segment
+            if (c.cp_pos <= L.hi_rel) {
+                cp_catch_up(c, min(L.hi_rel, c.limit));
+                si.cont_tail = c.cp_cont;
+            } else {
+                uint32_t n = c.cp_cont;
+                for (uint32_t p = L.hi_rel; p < c.cp_pos; p++) n -= (ld_u8(c.base + p) & 0xC0u) == 0x80u;
+                si.cont_tail = n;
+            }
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
+        dst[0] = make_uint4(si.spec_state, si.end_state, si.end_over, si.head_count);
+        dst[1] = make_uint4(si.drop, si.cont_tail, 0u, 0u);
+        out.unit_counts[2 * L.seg] = 0;
+        out.unit_counts[2 * L.seg + 1] = c.nemit;
+        L.done = 1;
+    }
+}
+
+// Runs the exact scanner until the lane is at a point where the fast path can take over
+// (16-byte aligned, hot state, nothing pending, inside a piece) or the segment is finished.
+template <int MODE, bool CP>
+__device__ __noinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im, const Batch &B, const Sink &out,
+                                    SegInfo *seg_info, HotMap hm, uint32_t min_at) {
+    for (;;) {
+        exact_scan<MODE, CP>(c, im, out, true, min_at, 0, hm);
+        if (c.at >= c.stop && (MODE != kModeLeftmost || !c.have)) {
+            advance_piece<MODE, CP>(c, L, B, out, seg_info);
+            if (L.done) return;
+            min_at = c.at;
+            continue;
+        }
+        return;
+    }
+}
+
 template <int MODE, bool CP, int COLMODE>
 __global__ void __launch_bounds__(1024, 1)
-scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, uint32_t hot_bytes,
-                   unsigned int *task_counter, unsigned long long *trap_stats) {
+scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, SegInfo *seg_info, uint32_t H,
+                   uint32_t hot_bytes, unsigned int *task_counter, unsigned long long *trap_stats) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *hot = smem;
     uint8_t *cmap = smem + hot_bytes;                     // 256 B
@@ -154,46 +272,80 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, u
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint8_t *stage = stage_all + (size_t)warp * 2 * kStageBytes;
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
-    const uintptr_t gbase = reinterpret_cast<uintptr_t>(U.bytes) & ~uintptr_t(kChunk - 1);
+    const uintptr_t gbase = reinterpret_cast<uintptr_t>(B.bytes + P.origin);  // 64-byte aligned by construction of the plan
     const uint32_t my_swz = (lane >> 1) & 3;
+    const uint64_t q = P.lane_stride;
+    const uint64_t n_tasks = ((uint64_t)P.n_segments + 32 * q - 1) / (32 * q) * q;
+    const int64_t stream_lo = __ldg(B.offsets), stream_hi = __ldg(B.offsets + B.n_haystacks);
 
     for (;;) {
-        // ---- claim the next 32 units -------------------------------------------
+        // ---- claim the next warp-task: 32 segments, lane_stride apart -----------------
         unsigned int task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
-        if ((int64_t)task * 32 >= U.n_units) break;
+        if (task >= n_tasks) break;
 
-        UnitCtx c;
-        const bool valid = init_unit<CP>(c, U, (int64_t)task * 32 + lane);
-        uint32_t phase = 0, off16 = 0, nchunks = 0;
-        uint32_t rel0 = 0;      // position (relative to c.base, mod 2^32) of the first byte of chunk 0
-        uint32_t pos = 0, s = 0;
-        uint32_t fast_last = 0;  // last position a 16-byte fast group may start at
-        bool fast_ok = false;
-        uint32_t cpd = 0;        // code points: pos - (code points before pos)
-        uint32_t end = 0;
-        if (valid) {
-            const uintptr_t p0 = reinterpret_cast<uintptr_t>(c.base + c.at);
-            const uintptr_t pe = reinterpret_cast<uintptr_t>(c.base + c.end);
-            const uintptr_t a0 = p0 & ~uintptr_t(kChunk - 1);
-            phase = (uint32_t)(0 - reinterpret_cast<uintptr_t>(c.base)) & 15u;
+        PieceCtx c;
+        LaneSeg L;
+        L.seg = (int64_t)(((uint64_t)(task / q) * 32 + lane) * q + task % q);
+        L.done = 1;
+        L.spec_state = kNoState;
+        L.head_count = 0;
+        uint32_t off16 = 0, nchunks = 0, rel0 = 0;
+        uint32_t pos = 0, s = 0, stop = 0, cpd = 0;
+        const int64_t glo = P.origin + L.seg * (int64_t)P.seg_bytes;
+        const int64_t lo = max(glo, stream_lo), hi = min(glo + (int64_t)P.seg_bytes, stream_hi);
+        if (L.seg < P.n_segments && lo >= hi) {
+            // a segment outside the stream (the plan is sized from the buffer length): nothing to scan
+            uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
+            dst[0] = make_uint4(kNoState, kRoot, 0u, 0u);
+            dst[1] = make_uint4(0u, 0u, 0u, 0u);
+            out.unit_counts[2 * L.seg] = 0;
+            out.unit_counts[2 * L.seg + 1] = 0;
+        } else if (L.seg < P.n_segments) {
+            const int64_t h = find_haystack(B, lo);
+            const int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);
+            const bool cont = hs < lo;
+            const int64_t w = cont ? max(hs, lo - (int64_t)P.warm) : lo;
+            const uintptr_t pw = reinterpret_cast<uintptr_t>(B.bytes + w);
+            const uintptr_t a0 = pw & ~uintptr_t(kChunk - 1);
+            L.org = w - (int64_t)(pw - a0);
+            L.lo_rel = (uint32_t)(lo - L.org);
+            L.hi_rel = (uint32_t)(hi - L.org);
+            L.h = (uint32_t)h;
+            L.kind = cont ? kPieceWarm : kPieceNormal;
+            L.done = 0;
             off16 = (uint32_t)((a0 - gbase) >> 4);
-            nchunks = (pe > a0) ? (uint32_t)((pe - a0 + kChunk - 1) / kChunk) : 0;
-            rel0 = c.at - (uint32_t)(p0 - a0);
-            // head: bytes before the first 16-byte boundary
-            exact_scan<MODE, CP>(c, im, out, true, c.at, phase, hm);
+            nchunks = (L.hi_rel + kChunk - 1) / kChunk;
+            rel0 = 0;
+            c.base = B.bytes + L.org;
+            c.at = (uint32_t)(w - L.org);
+            c.limit = (uint32_t)(he - L.org);
+            c.stop = cont ? L.lo_rel : min(L.hi_rel, c.limit);
+            c.emit_from = cont ? 0xffffffffu : 0u;  // the warm-up reports nothing
+            c.state = kRoot;
+            c.have = 0;
+            c.last_pid = c.last_end = 0;
+            c.hay = (uint32_t)h;
+            c.hay_delta = (uint32_t)(L.org - hs);
+            c.unit = (uint32_t)(2 * L.seg + 1);
+            c.nemit = 0;
+            c.cp_pos = c.at;
+            c.cp_cont = 0;
+            // bytes before the first 16-byte boundary, pieces shorter than that, ...
+            settle<MODE, CP>(c, L, im, B, out, seg_info, hm, c.at);
             pos = c.at;
-            end = c.end;
-            s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;  // a hot row unless the unit is already finished
-            if (CP) {
-                cp_catch_up(c, pos);
-                cpd = pos - c.cp_count;
+            stop = c.stop;
+            if (!L.done) {
+                s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
+                if (CP) {
+                    cp_catch_up(c, pos);
+                    cpd = c.cp_cont;
+                }
             }
-            fast_ok = end >= 16 && pos < end;
-            fast_last = end - 16;
         }
-        uint32_t kmax = nchunks;
+        bool done = L.done != 0;
+        uint32_t kmax = done ? 0u : nchunks;
 #pragma unroll
         for (int d = 16; d; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
 
@@ -203,7 +355,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, u
         for (int i = 0; i < 4; i++) {
             const uint32_t idx = i * 32 + lane, ch = idx >> 2, un = idx & 3;
             src_off16[i] = __shfl_sync(0xffffffffu, off16, ch) + un;
-            src_nch[i] = __shfl_sync(0xffffffffu, nchunks, ch);
+            src_nch[i] = __shfl_sync(0xffffffffu, done ? 0u : nchunks, ch);
             dst_off[i] = ch * kChunk + ((un ^ ((ch >> 1) & 3)) << 4);
         }
         auto issue = [&](uint32_t k) {
@@ -214,6 +366,26 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, u
                 cp_async16(buf + dst_off[i], src, k < src_nch[i] ? 16u : 0u);
             }
             cp_async_commit();
+        };
+        // hand the lane over to the exact scanner at position `pos`, come back at the next fast-resume point
+        auto leave_fast = [&](uint32_t min_at) {
+            c.state = __ldg(hot_img.hot2full + s / row_bytes);
+            c.at = pos;
+            if (CP) {
+                c.cp_pos = pos;
+                c.cp_cont = cpd;
+            }
+            settle<MODE, CP>(c, L, im, B, out, seg_info, hm, min_at);
+            done = L.done != 0;
+            pos = c.at;
+            stop = c.stop;
+            if (!done) {
+                s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
+                if (CP) {
+                    cp_catch_up(c, pos);
+                    cpd = c.cp_cont;
+                }
+            }
         };
 
         __syncwarp();  // previous task's readers are done with both buffers
@@ -226,8 +398,12 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, u
             const uint32_t relk = rel0 + k * kChunk;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                const uint32_t g = relk + j * 16;  // wraps for positions before the unit: never equal to pos then
-                if (fast_ok && g == pos && g <= fast_last) {
+                const uint32_t g = relk + j * 16;
+                while (!done && g == pos) {
+                    if (g + 16 > stop) {
+                        leave_fast(stop);  // the piece ends inside this group: finish it exactly, start the next one
+                        continue;
+                    }
                     const uint4 w = *reinterpret_cast<const uint4 *>(buf + ((j ^ my_swz) << 4));
                     uint32_t t = fstep4<COLMODE>(s, w.x, ft);
                     t = fstep4<COLMODE>(t, w.y, ft);
@@ -244,37 +420,13 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Units U, Sink out, uint32_t H, u
                     } else {
                         // something happened in these 16 bytes: redo them exactly
                         n_traps++;
-                        c.state = __ldg(hot_img.hot2full + s / row_bytes);
-                        c.at = pos;
-                        if (CP) {
-                            c.cp_pos = pos;
-                            c.cp_count = pos - cpd;
-                        }
-                        exact_scan<MODE, CP>(c, im, out, true, pos + 16, phase, hm);
-                        s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
-                        pos = c.at;
-                        if (CP) {
-                            cp_catch_up(c, pos);
-                            cpd = pos - c.cp_count;
-                        }
-                        fast_ok = pos < end;
+                        leave_fast(pos + 16);
                     }
                 }
             }
         }
-        if (valid) {
-            // tail: whatever is left after the last full 16-byte group
-            if (pos < end) {
-                c.state = __ldg(hot_img.hot2full + s / row_bytes);
-                c.at = pos;
-                if (CP) {
-                    c.cp_pos = pos;
-                    c.cp_count = pos - cpd;
-                }
-                exact_scan<MODE, CP>(c, im, out, false, 0, 0, hm);
-            }
-            out.unit_counts[c.unit] = c.nemit;
-        }
+        // whatever is left (nothing, normally): exact to the end of the segment
+        while (!done) leave_fast(stop);
     }
     // how well the hot set fits the data: the host re-profiles when traps are frequent
 #pragma unroll

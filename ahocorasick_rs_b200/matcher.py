@@ -54,9 +54,6 @@ class _Automaton:
     """Owns the host automaton handle, its device image and a growable device
     workspace.  Shared by both public classes."""
 
-    CHUNK_BYTES = 4096          # unit size for chunked overlapping scans of one large haystack
-    CHUNKED_MIN_BYTES = 1 << 16
-
     def __init__(self, pattern_bytes: Sequence[bytes], matchkind: MatchKind, implementation: Optional[Implementation]):
         L = _capi.lib()
         n = len(pattern_bytes)
@@ -79,6 +76,7 @@ class _Automaton:
         self._images = {}      # device index -> uint8 tensor
         self._hot = {}         # device index -> dict(tensor, rows, reprofile, calls, backoff)
         self._ws = {}          # device index -> dict of tensors
+        self.last_stats = {}
         self._lock = threading.Lock()
 
     def __del__(self):
@@ -130,13 +128,12 @@ class _Automaton:
         idx = device.index
         st = self._hot.get(idx)
         need = st is None or st["reprofile"]
-        if need and data is not None and data.numel() > 0:
+        if need and data is not None and data.numel() > 0 and offsets is not None and offsets.numel() > 1:
             img = self.image(device)
             visits = torch.empty(self.num_states, dtype=torch.int32, device=device)
             stream = torch.cuda.current_stream(device).cuda_stream
-            n = 0 if offsets is None else offsets.numel() - 1
-            rc = self._L.acb_profile(self._h, img.data_ptr(), data.data_ptr(),
-                                     None if offsets is None else offsets.data_ptr(), n, data.numel(),
+            n = offsets.numel() - 1
+            rc = self._L.acb_profile(self._h, img.data_ptr(), data.data_ptr(), offsets.data_ptr(), n, data.numel(),
                                      int(bool(overlapping)), visits.data_ptr(), stream)
             if rc != _capi.ACB_OK:
                 raise RuntimeError(_capi.last_error())
@@ -157,24 +154,39 @@ class _Automaton:
             st["reprofile"] = True
             st["calls"] = 0
 
-    def _workspace(self, device, n_units: int, capacity: int):
+    def _plan(self, data, n_haystacks: int):
+        plan = _capi.Plan()
+        rc = self._L.acb_plan_scan(self._h, data.data_ptr(), data.numel(), n_haystacks, C.byref(plan))
+        if rc != _capi.ACB_OK:
+            raise RuntimeError(_capi.last_error())
+        return plan
+
+    def _workspace(self, device, plan, n_haystacks: int, capacity: int):
         torch = _torch()
         idx = device.index
         ws = self._ws.get(idx)
-        if ws is None or ws["n_units"] < n_units or ws["capacity"] < capacity:
-            n_alloc = max(n_units, ws["n_units"] if ws else 0, 1)
+        need = (ws is None or ws["n_units"] < plan.n_units or ws["n_segments"] < plan.n_segments or
+                ws["scratch"].numel() < plan.scratch_words or ws["n_haystacks"] < n_haystacks or ws["capacity"] < capacity)
+        if need:
+            n_units = max(plan.n_units, ws["n_units"] if ws else 0, 1)
+            n_seg = max(plan.n_segments, ws["n_segments"] if ws else 0, 1)
+            n_hay = max(n_haystacks, ws["n_haystacks"] if ws else 0, 1)
+            n_scr = max(plan.scratch_words, ws["scratch"].numel() if ws else 0, 16)
             cap = max(capacity, ws["capacity"] if ws else 0, 1024)
             dev = torch.device("cuda", idx)
             ws = {
-                "n_units": n_alloc, "capacity": cap,
+                "n_units": n_units, "n_segments": n_seg, "n_haystacks": n_hay, "capacity": cap,
                 "raw": torch.empty((cap, 4), dtype=torch.int32, device=dev),
                 "raw_seq": torch.empty(cap, dtype=torch.int32, device=dev),
                 "raw_unit": torch.empty(cap, dtype=torch.int32, device=dev),
-                "unit_counts": torch.empty(n_alloc, dtype=torch.int32, device=dev),
-                "unit_offsets": torch.empty(n_alloc + 1, dtype=torch.int64, device=dev),
-                "scratch": torch.empty(int(self._L.acb_scratch_words(n_alloc)), dtype=torch.int64, device=dev),
-                "total": torch.zeros(4, dtype=torch.int64, device=dev),
+                "raw_aux": torch.empty(cap, dtype=torch.int32, device=dev),
+                "unit_counts": torch.empty(n_units, dtype=torch.int32, device=dev),
+                "unit_offsets": torch.empty(n_units + 1, dtype=torch.int64, device=dev),
+                "seg_info": torch.empty((n_seg, 8), dtype=torch.int32, device=dev),
+                "scratch": torch.empty(n_scr, dtype=torch.int64, device=dev),
+                "total": torch.zeros(8, dtype=torch.int64, device=dev),
                 "out": torch.empty((cap, 4), dtype=torch.int32, device=dev),
+                "match_offsets": torch.empty(n_hay + 1, dtype=torch.int64, device=dev),
             }
             self._ws[idx] = ws
         return ws
@@ -184,13 +196,16 @@ class _Automaton:
         s.dev_raw = ws["raw"].data_ptr()
         s.dev_raw_seq = ws["raw_seq"].data_ptr()
         s.dev_raw_unit = ws["raw_unit"].data_ptr()
+        s.dev_raw_aux = ws["raw_aux"].data_ptr()
         s.raw_capacity = ws["capacity"]
         s.dev_unit_counts = ws["unit_counts"].data_ptr()
         s.dev_unit_offsets = ws["unit_offsets"].data_ptr()
+        s.dev_seg_info = ws["seg_info"].data_ptr()
         s.dev_scratch = ws["scratch"].data_ptr()
         s.dev_total = ws["total"].data_ptr()
         s.dev_out = ws["out"].data_ptr()
         s.out_capacity = ws["capacity"]
+        s.dev_match_offsets = ws["match_offsets"].data_ptr()
         return s
 
     def check_overlapping(self, overlapping: bool):
@@ -202,65 +217,43 @@ class _Automaton:
     def scan_device(self, data, offsets, overlapping=False, codepoints=False, capacity: Optional[int] = None,
                     sync: bool = True):
         """Scan a device-resident batch.  data: uint8 CUDA tensor, offsets: int64
-        CUDA tensor (n+1).  Returns (matches, match_offsets, total): matches is an
-        int32 CUDA tensor (total, 4) = (haystack, pattern, start, end) in the
-        reference's order, match_offsets (n+1) brackets each haystack's rows.
-        With sync=False the call returns right after enqueueing (total is a
-        device tensor and matches is the whole capacity-sized buffer)."""
+        CUDA tensor (n+1).  One haystack of any size is simply n = 1.  Returns
+        (matches, match_offsets, total): matches is an int32 CUDA tensor
+        (total, 4) = (haystack, pattern, start, end) in the reference's order,
+        match_offsets (n+1) brackets each haystack's rows.  With sync=False the
+        call returns right after enqueueing (total is the 8-entry device status
+        tensor and matches the whole capacity-sized buffer)."""
         torch = _require_cuda()
         self.check_overlapping(overlapping)
         dev = data.device
         n = offsets.numel() - 1
+        if data.numel() >= (1 << 32) - 256:
+            raise ValueError("buffers of 4 GiB and more are not supported yet (32-bit match offsets)")
         img = self.image(dev)
         cap = capacity or max(1024, n * 2)
         stream = torch.cuda.current_stream(dev).cuda_stream
         with self._lock, torch.cuda.device(dev):
             hot = self.hot(dev, data, offsets, overlapping)
+            plan = self._plan(data, n)
             while True:
-                ws = self._workspace(dev, n, cap)
+                ws = self._workspace(dev, plan, n, cap)
                 st = self._ws_struct(ws)
                 rc = self._L.acb_scan_batch(self._h, img.data_ptr(), hot["tensor"].data_ptr(), hot["rows"],
-                                            data.data_ptr(), offsets.data_ptr(), n,
-                                            int(bool(overlapping)), int(bool(codepoints)), C.byref(st), stream)
+                                            data.data_ptr(), offsets.data_ptr(), n, data.numel(),
+                                            int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
                     err = _capi.last_error()
                     raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
                 if not sync:
-                    return ws["out"], ws["unit_offsets"][: n + 1], ws["total"]
+                    return ws["out"], ws["match_offsets"][: n + 1], ws["total"]
                 tot = ws["total"].tolist()
-                total = tot[0]
+                total, complete, raw_total = tot[0], tot[1], tot[4]
                 self._note_trap_stats(hot, tot[2], tot[3])
-                if total <= ws["capacity"]:
-                    return ws["out"][:total], ws["unit_offsets"][: n + 1], total
-                cap = total + total // 8 + 16
-
-    def scan_chunked_device(self, data, codepoints=False, chunk_bytes: Optional[int] = None):
-        """Overlapping scan of ONE device-resident haystack, chunk-parallel."""
-        torch = _require_cuda()
-        self.check_overlapping(True)
-        dev = data.device
-        chunk = chunk_bytes or self.CHUNK_BYTES
-        n_units = int(self._L.acb_chunk_count(data.numel(), chunk))
-        img = self.image(dev)
-        cap = max(1024, n_units)
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        with self._lock, torch.cuda.device(dev):
-            hot = self.hot(dev, data, None, True)
-            while True:
-                ws = self._workspace(dev, n_units, cap)
-                st = self._ws_struct(ws)
-                rc = self._L.acb_scan_chunked(self._h, img.data_ptr(), hot["tensor"].data_ptr(), hot["rows"],
-                                              data.data_ptr(), data.numel(), chunk,
-                                              int(bool(codepoints)), C.byref(st), stream)
-                if rc != _capi.ACB_OK:
-                    err = _capi.last_error()
-                    raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
-                tot = ws["total"].tolist()
-                total = tot[0]
-                self._note_trap_stats(hot, tot[2], tot[3])
-                if total <= ws["capacity"]:
-                    return ws["out"][:total], total
-                cap = total + total // 8 + 16
+                self.last_stats = {"groups": tot[2], "traps": tot[3], "repairs": tot[5], "segments": plan.n_segments,
+                                   "segment_bytes": plan.segment_bytes, "lane_stride": plan.lane_stride}
+                if complete or (total == 0 and raw_total == 0):
+                    return ws["out"][:total], ws["match_offsets"][: n + 1], total
+                cap = max(total, raw_total) + max(total, raw_total) // 8 + 16
 
     def scan_host_batch(self, chunks: Sequence[bytes], overlapping: bool, codepoints: bool):
         """Host buffers in, host numpy out: (matches uint32 (k,4), match_offsets int64 (n+1))."""
@@ -271,8 +264,6 @@ class _Automaton:
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
         total_bytes = int(offs[-1])
-        if total_bytes >= (1 << 32) - 1 and n == 1:
-            raise ValueError("haystacks of 4 GiB and more are not supported yet")
         dev = torch.device("cuda", torch.cuda.current_device())
         host = torch.empty(max(total_bytes, 1), dtype=torch.uint8, pin_memory=True)
         hv = host.numpy()
@@ -281,10 +272,7 @@ class _Automaton:
             ln = len(c)
             hv[pos:pos + ln] = np.frombuffer(c, dtype=np.uint8)
             pos += ln
-        d_data = host.to(dev, non_blocking=True)
-        if n == 1 and overlapping and total_bytes >= self.CHUNKED_MIN_BYTES:
-            m, total = self.scan_chunked_device(d_data[:total_bytes], codepoints)
-            return m.cpu().numpy().view(np.uint32), np.array([0, total], dtype=np.int64)
+        d_data = host.to(dev, non_blocking=True)[:total_bytes]
         d_offs = torch.from_numpy(offs).to(dev, non_blocking=True)
         m, moffs, _ = self.scan_device(d_data, d_offs, overlapping, codepoints)
         return m.cpu().numpy().view(np.uint32), moffs.cpu().numpy()

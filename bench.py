@@ -198,6 +198,7 @@ def main():
         step(i)
     torch.cuda.synchronize()
     totals = [int(ac.scan_device(*d_batches[b], capacity=cap)[2]) for b in range(2)]
+    scan_stats = dict(ac._ac.last_stats)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -285,6 +286,7 @@ def main():
                 "h2d_bytes_per_step": bytes_per_step + 8 * (n_hay + 1), "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps, "api": "AhoCorasick.scan_device on pinned host tensors copied H2D inside the timed region, matches copied back"},
         "gpu_launches": launches,
+        "scan_stats": scan_stats,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:

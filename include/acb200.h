@@ -104,39 +104,62 @@ int acb_image_write(const acb_automaton *a, void *host_dst, uint64_t dst_bytes);
  * with its row count, to the scans.  Which rows are hot changes speed only --
  * everything the fast path cannot prove uneventful is redone by the exact
  * scanner -- never results.  dev_hot == NULL selects the plain kernel.
- * For acb_profile pass dev_offsets == NULL and len for one large haystack.
  */
 int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *dev_bytes, const int64_t *dev_offsets,
-                int64_t n_haystacks, uint64_t len, int overlapping, uint32_t *dev_visits, void *stream);
+                int64_t n_haystacks, uint64_t total_bytes, int overlapping, uint32_t *dev_visits, void *stream);
 uint64_t acb_hot_bytes(const acb_automaton *a, uint32_t max_rows);
 int acb_hot_build(const acb_automaton *a, const uint32_t *host_visits, uint32_t max_rows, void *host_dst,
                   uint64_t dst_bytes);
 uint32_t acb_hot_rows(const void *host_hot);
 
 /*
- * Caller-provided device workspace for one scan.  n_units = number of scan
- * units: haystacks for acb_scan_batch, chunks for acb_scan_chunked
- * (acb_chunk_count()).
+ * How a scan is cut up.  The byte stream [offsets[0], offsets[n]) is divided into
+ * fixed-size SEGMENTS on a grid anchored at the 64-byte aligned address at or
+ * before dev_bytes; one GPU lane scans one segment, so the work per lane is the
+ * same whatever the haystack lengths are (one huge haystack, a ragged batch, a
+ * million short lines).  A segment that begins inside a haystack starts from a
+ * speculated automaton state that is verified -- and, when wrong, repaired --
+ * before results are delivered; see DESIGN.md.  The plan depends only on
+ * host-known quantities: the automaton, the address of the byte buffer, its
+ * length and the number of haystacks.
  */
+typedef struct acb_plan {
+    uint64_t n_segments;
+    uint64_t n_units;       /* entries the unit arrays of the workspace need */
+    uint64_t scratch_words; /* u64 words dev_scratch needs */
+    uint32_t segment_bytes;
+    uint32_t warm_bytes;    /* bytes scanned before a segment to guess its start state (>= longest pattern) */
+    uint32_t lane_stride;   /* segments between neighbouring lanes of a warp */
+    uint32_t reserved;
+} acb_plan;
+
+int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_bytes, uint64_t n_haystacks,
+                  acb_plan *plan);
+
+/* Caller-provided device workspace for one scan, sized from the plan. */
 typedef struct acb_workspace {
     acb_match *dev_raw;      /* [raw_capacity] unordered matches as kernels emit them */
     uint32_t *dev_raw_seq;   /* [raw_capacity] rank of each raw match inside its unit */
-    uint32_t *dev_raw_unit;  /* [raw_capacity] unit each raw match belongs to */
+    uint32_t *dev_raw_unit;  /* [raw_capacity] unit (segment slot / haystack) each raw match belongs to */
+    uint32_t *dev_raw_aux;   /* [raw_capacity] code point bookkeeping per raw match */
     uint64_t raw_capacity;
-    uint32_t *dev_unit_counts;  /* [n_units] matches per unit (output) */
-    uint64_t *dev_unit_offsets; /* [n_units + 1] exclusive prefix sum of the counts (output) */
-    uint64_t *dev_scratch;      /* [acb_scratch_words(n_units)] */
-    uint64_t *dev_total;        /* [4]: [0] = matches found, [1] = matches delivered in dev_out (0 = incomplete),
-                                   [2] = 16-byte groups the fast path tried, [3] = groups it had to hand to the exact scanner */
-    acb_match *dev_out;         /* [out_capacity] final matches in the reference's order */
+    uint32_t *dev_unit_counts;   /* [plan.n_units] */
+    uint64_t *dev_unit_offsets;  /* [plan.n_units + 1] */
+    void *dev_seg_info;          /* [plan.n_segments * 32 bytes] per-segment summaries */
+    uint64_t *dev_scratch;       /* [plan.scratch_words] */
+    uint64_t *dev_total;         /* [8]: [0] = matches found, [1] = 1 when dev_out holds all of them (0: buffers too
+                                    small, retry), [2] = 16-byte groups the fast path tried, [3] = groups handed to the
+                                    exact scanner, [4] = raw matches emitted, [5] = segment boundaries repaired */
+    acb_match *dev_out;          /* [out_capacity] final matches in the reference's order */
     uint64_t out_capacity;
+    uint64_t *dev_match_offsets; /* [n_haystacks + 1] haystack h's matches are dev_out[off[h] .. off[h+1]) */
 } acb_workspace;
-
-uint64_t acb_scratch_words(uint64_t n_units);
 
 /*
  * Scan a batch of haystacks resident in device memory:
- * haystack h = dev_bytes[dev_offsets[h] .. dev_offsets[h+1]).
+ * haystack h = dev_bytes[dev_offsets[h] .. dev_offsets[h+1]); total_bytes =
+ * length of the dev_bytes buffer (>= dev_offsets[n]).  One haystack of many
+ * gigabytes is just n_haystacks = 1.
  *
  * Per haystack this is the drain of the reference's iterator: get_matches
  * (src/lib.rs:42-68) choosing try_find_iter (58-60) or
@@ -146,29 +169,16 @@ uint64_t acb_scratch_words(uint64_t n_units);
  *
  * On return (after the stream has run): ws->dev_out holds
  * min(total, out_capacity) matches ordered by haystack and then in the
- * reference's iteration order; ws->dev_unit_offsets[h..h+1] brackets haystack
- * h's matches; ws->dev_total[0] is the true total.  If total exceeds
- * raw_capacity or out_capacity nothing is lost silently: dev_total[0] says how
- * much room a second call needs.
+ * reference's iteration order; ws->dev_match_offsets brackets each haystack's
+ * matches; ws->dev_total[0] is the true total.  If the matches did not fit
+ * raw_capacity / out_capacity nothing is lost silently: dev_total[1] is 0 and
+ * dev_total[0] / [4] say how much room a second call needs.
  * overlapping on a non-Standard automaton returns ACB_EUNSUPPORTED before any
  * byte is read, like the reference.
  */
 int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
-                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, int overlapping,
-                   int codepoints, const acb_workspace *ws, void *stream);
-
-/*
- * Scan ONE large device-resident haystack, split into fixed-size chunks that
- * are scanned in parallel.  overlapping must be non-zero (position-local, so
- * chunking with a halo of max_pattern_len-1 bytes is exact); the serial
- * restart rule of non-overlapping search is served by acb_scan_batch with
- * n_haystacks = 1.  Output order = the reference's (end, start, pattern).
- * Units are chunks: acb_chunk_count(len, chunk_bytes).
- */
-uint64_t acb_chunk_count(uint64_t len, uint32_t chunk_bytes);
-int acb_scan_chunked(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
-                     const uint8_t *dev_bytes, uint64_t len, uint32_t chunk_bytes, int codepoints,
-                     const acb_workspace *ws, void *stream);
+                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
+                   int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream);
 
 /* Kernel launch bookkeeping for bench.py's "gpu_launches". */
 uint64_t acb_launch_count(void);
@@ -184,9 +194,10 @@ int acb_timing_read(double *total_ms, uint64_t *n_scans);
 
 /* Tuning knobs (0 = library default). Affects speed only, never results. */
 typedef struct acb_tuning {
-    int kernel;        /* 0 auto, 1 = plain (table in global/L2), 2 = staged (hot rows in shared memory) */
+    int kernel;        /* 0 auto, 1 = plain (one thread per haystack, table in global/L2), 2 = staged segments */
     int hot_rows;      /* cap on rows kept in shared memory */
-    int ctas_per_sm;   /* persistent grid = ctas_per_sm * SM count */
+    int segment_bytes; /* segment size (rounded up to a multiple of 64 and to 8 x the warm-up) */
+    int reserved;
 } acb_tuning;
 int acb_set_tuning(const acb_tuning *t);
 

@@ -43,8 +43,14 @@ def test_build_and_image_roundtrip_without_gpu():
     bad = np.array([0, 5, 5, 14], dtype=np.uint64)  # an empty pattern
     assert L.acb_build(blob.ctypes.data, bad.ctypes.data, 3, 0, -1, C.byref(h)) == _capi.ACB_EBUILD
     assert b"empty pattern" in L.acb_last_error()
-    assert L.acb_scratch_words(100_000) > 100_000
-    assert L.acb_chunk_count(10_000, 4096) == 3
+    plan = _capi.Plan()
+    assert L.acb_build(blob.ctypes.data, offs.ctypes.data, 3, 0, -1, C.byref(h)) == 0
+    assert L.acb_plan_scan(h, 64 + 5, 409_600_000, 100_000, C.byref(plan)) == 0
+    assert plan.segment_bytes == 1024 and plan.warm_bytes == 16 and plan.lane_stride == 4
+    assert plan.n_segments == (409_600_000 + 5 + 1023) // 1024 and plan.n_units == 2 * plan.n_segments
+    assert plan.scratch_words > plan.n_segments
+    assert L.acb_plan_scan(h, 0, 1 << 20, 1, C.byref(plan)) == 0 and plan.lane_stride == 1
+    L.acb_free(h)
 
 
 def test_constructor_errors_like_the_reference():

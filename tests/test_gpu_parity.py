@@ -23,19 +23,21 @@ with open(os.path.join(HERE, "golden", "reference_vectors.json"), encoding="utf-
     VECTORS = json.load(f)["vectors"]
 
 
-def set_kernel(kernel=0, hot_rows=0):
-    t = _capi.Tuning(kernel, hot_rows, 0)
+def set_kernel(kernel=0, hot_rows=0, segment_bytes=0):
+    t = _capi.Tuning(kernel, hot_rows, segment_bytes, 0)
     assert _capi.lib().acb_set_tuning(C.byref(t)) == 0
 
 
-@pytest.fixture(params=["staged", "plain", "staged-tiny-hot"])
+@pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments"])
 def kernel(request):
     if request.param == "plain":
         set_kernel(1)
     elif request.param == "staged":
         set_kernel(2)
-    else:
+    elif request.param == "staged-tiny-hot":
         set_kernel(2, 5)  # 5 hot rows: nearly every group traps, exercising the exact/fast hand-over
+    else:
+        set_kernel(2, 0, 128)  # 128-byte segments: speculative starts and the repair pass everywhere
     yield request.param
     set_kernel(0)
 
@@ -132,13 +134,36 @@ def test_config4_shape_scaled_chunked_overlapping(kernel):
     orc = Oracle(pats, "Standard")
     exp = orc.find(data.tobytes(), overlapping=True)
     ac = BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA)
-    for chunk in (4096, 1000):
-        m, total = ac._ac.scan_chunked_device(dev(data), chunk_bytes=chunk)
-        got = m.cpu().numpy().view(np.uint32)
-        assert total == len(exp)
-        assert [tuple(int(x) for x in r[1:]) for r in got] == exp
+    m, moffs, total = ac.scan_device(dev(data), dev(np.array([0, len(data)], dtype=np.int64)), overlapping=True)
+    got = m.cpu().numpy().view(np.uint32)
+    assert total == len(exp) and moffs.tolist() == [0, total]
+    assert [tuple(int(x) for x in r[1:]) for r in got] == exp
     # the drop-in call takes the same path for a large haystack
     assert ac.find_matches_as_indexes(data.tobytes(), overlapping=True) == exp
+
+
+@pytest.mark.parametrize("kind", KINDS, ids=lambda k: k.name)
+def test_one_large_haystack_non_overlapping(kind, kernel):
+    """One multi-megabyte haystack, non-overlapping: segments of the SAME haystack are scanned in
+    parallel from speculated states and must still give the serial (restart-at-match-end) answer."""
+    rng = np.random.default_rng(21)
+    pats = sorted({bytes(rng.integers(97, 101, size=rng.integers(2, 7)).astype(np.uint8)) for _ in range(300)})
+    data = rng.integers(97, 101, size=1_500_003, dtype=np.uint8).astype(np.uint8)
+    exp = Oracle(pats, kind.name).find(data.tobytes())
+    assert len(exp) > 10_000
+    ac = BytesAhoCorasick(pats, kind)
+    assert ac.find_matches_as_indexes(data.tobytes()) == exp
+    if kernel != "plain":
+        assert ac._ac.last_stats["segments"] > 1000
+
+
+def test_dense_self_overlapping_matches_single_haystack(kernel):
+    """'aa' on a run of 'a' at an odd offset: every guessed restart phase is wrong and the
+    repair pass has to carry the truth through the whole haystack."""
+    for lead in (1, 2):
+        hay = b"b" * lead + b"a" * 20_001
+        exp = Oracle([b"aa"], "Standard").find(hay)
+        assert BytesAhoCorasick([b"aa"]).find_matches_as_indexes(hay) == exp
 
 
 def test_unaligned_base_and_tiny_haystacks(kernel):
@@ -189,7 +214,7 @@ def test_full_size_properties_config2():
     m = m.cpu().numpy().view(np.uint32).copy()
     moffs = moffs.cpu().numpy().copy()
     half = 10_000
-    m1, o1, t1 = ac.scan_device(d[: offs[half]], o[: half + 1])
+    m1, o1, t1 = ac.scan_device(d[: offs[half]], o[: half + 1].clone())
     m1 = m1.cpu().numpy().view(np.uint32).copy()
     m2, o2, t2 = ac.scan_device(d[offs[half]:], dev(offs[half:] - offs[half]))
     m2 = m2.cpu().numpy().view(np.uint32).copy()
