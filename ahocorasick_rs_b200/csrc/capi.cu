@@ -599,6 +599,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         P.warm = plan->warm_bytes;
         P.n_segments = (int64_t)plan->n_segments;
         P.lane_stride = plan->lane_stride;
+        P.avg_len = n_haystacks > 0 ? total_bytes / (uint64_t)n_haystacks : 0;
         n_units = 2 * plan->n_segments;
         rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st);
         if (rc) return rc;

@@ -57,6 +57,7 @@ struct SegPlan {
     uint32_t warm;        // multiple of 16, >= max_pattern_len - 1
     int64_t n_segments;
     uint32_t lane_stride;  // lane l of warp-task (a, j) scans segment (32 a + l) * lane_stride + j
+    uint64_t avg_len;      // hint: total bytes / haystacks (exact for equal-length batches): O(1) haystack lookup
 };
 
 // Per-segment summary written by the scan kernel, read by validate/repair and the ordering pass.

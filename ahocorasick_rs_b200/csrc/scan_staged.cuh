@@ -15,9 +15,10 @@
 //        (cp.async.bulk + mbarrier) when the whole hot image fits.
 //   [ column map : 256 B ]  (kColClass only)
 //   [ mbarrier ]
-//   [ staging : per warp, 2 buffers x 32 lanes x 64 B ]  lane l's 64-byte
-//        chunk, 16-byte units XOR-swizzled with (l >> 1) & 3 so the per-lane
-//        LDS.128 reads are bank-conflict free.
+//   [ staging : per warp, 2 buffers x 32 lanes x 80 B ]  lane l's 64-byte
+//        chunk at a pitch of 80 bytes: consecutive lanes start 5 sixteen-byte
+//        units apart, so the per-lane LDS.128 reads of a quarter warp hit 8
+//        different bank groups (conflict free) with plain immediate offsets.
 //
 // Work decomposition (scan_core.cuh: SegPlan).  The stream is cut into
 // fixed-size segments; a lane scans one segment, walking through whatever
@@ -41,7 +42,8 @@
 namespace acb {
 
 constexpr int kChunk = 64;                // bytes per lane per stage
-constexpr int kStageBytes = 32 * kChunk;  // per warp per buffer
+constexpr int kRow = kChunk + 16;         // a lane's row in the staging buffer: 80-byte pitch = conflict-free LDS.128 without a swizzle
+constexpr int kStageBytes = 32 * kRow;    // per warp per buffer
 constexpr int kStageOffset = 256 + 128;   // column map + mbarrier slot, after the hot table
 
 struct FastTab {
@@ -273,7 +275,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     uint8_t *stage = stage_all + (size_t)warp * 2 * kStageBytes;
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const uintptr_t gbase = reinterpret_cast<uintptr_t>(B.bytes + P.origin);  // 64-byte aligned by construction of the plan
-    const uint32_t my_swz = (lane >> 1) & 3;
+    // copy instruction i of a stage moves 16-byte unit (lane & 3) of lane (i * 8 + lane / 4)
+    const uint32_t cp_dst = stage_s + (lane >> 2) * kRow + (lane & 3) * 16;
     const uint64_t q = P.lane_stride;
     const uint64_t n_tasks = ((uint64_t)P.n_segments + 32 * q - 1) / (32 * q) * q;
     const int64_t stream_lo = __ldg(B.offsets), stream_hi = __ldg(B.offsets + B.n_haystacks);
@@ -291,8 +294,9 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         L.done = 1;
         L.spec_state = kNoState;
         L.head_count = 0;
-        uint32_t off16 = 0, nchunks = 0, rel0 = 0;
+        uint32_t off16 = 0, nchunks = 0;
         uint32_t pos = 0, s = 0, stop = 0, cpd = 0;
+        bool warm = false;  // the current piece is the silent warm-up before the segment
         const int64_t glo = P.origin + L.seg * (int64_t)P.seg_bytes;
         const int64_t lo = max(glo, stream_lo), hi = min(glo + (int64_t)P.seg_bytes, stream_hi);
         if (L.seg < P.n_segments && lo >= hi) {
@@ -303,8 +307,15 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             out.unit_counts[2 * L.seg] = 0;
             out.unit_counts[2 * L.seg + 1] = 0;
         } else if (L.seg < P.n_segments) {
-            const int64_t h = find_haystack(B, lo);
-            const int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);
+            // the haystack containing lo: try the position an equal-length batch would put it at, else search
+            int64_t h = P.avg_len ? (lo - stream_lo) / (int64_t)P.avg_len : 0;
+            if (h >= B.n_haystacks) h = B.n_haystacks - 1;
+            int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);
+            if (!(hs <= lo && lo < he)) {
+                h = find_haystack(B, lo);
+                hs = __ldg(B.offsets + h);
+                he = __ldg(B.offsets + h + 1);
+            }
             const bool cont = hs < lo;
             const int64_t w = cont ? max(hs, lo - (int64_t)P.warm) : lo;
             const uintptr_t pw = reinterpret_cast<uintptr_t>(B.bytes + w);
@@ -317,7 +328,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             L.done = 0;
             off16 = (uint32_t)((a0 - gbase) >> 4);
             nchunks = (L.hi_rel + kChunk - 1) / kChunk;
-            rel0 = 0;
             c.base = B.bytes + L.org;
             c.at = (uint32_t)(w - L.org);
             c.limit = (uint32_t)(he - L.org);
@@ -332,15 +342,24 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             c.nemit = 0;
             c.cp_pos = c.at;
             c.cp_cont = 0;
-            // bytes before the first 16-byte boundary, pieces shorter than that, ...
-            settle<MODE, CP>(c, L, im, B, out, seg_info, hm, c.at);
-            pos = c.at;
-            stop = c.stop;
-            if (!L.done) {
-                s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
-                if (CP) {
-                    cp_catch_up(c, pos);
-                    cpd = c.cp_cont;
+            warm = cont;
+            if ((c.at & 15u) == 0 && c.at + 16 <= c.stop) {
+                // starts on a 16-byte boundary in the root state (hot row 0): straight into the fast path
+                pos = c.at;
+                stop = c.stop;
+                s = 0;
+            } else {
+                // bytes before the first 16-byte boundary, pieces shorter than that, ...
+                settle<MODE, CP>(c, L, im, B, out, seg_info, hm, c.at);
+                pos = c.at;
+                stop = c.stop;
+                warm = !L.done && L.kind == kPieceWarm;
+                if (!L.done) {
+                    s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
+                    if (CP) {
+                        cp_catch_up(c, pos);
+                        cpd = c.cp_cont;
+                    }
                 }
             }
         }
@@ -348,22 +367,17 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         uint32_t kmax = done ? 0u : nchunks;
 #pragma unroll
         for (int d = 16; d; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+        if (done) nchunks = 0;
 
-        // who loads what: copy instruction i moves 16-byte unit (i*32+lane)&3 of lane (i*32+lane)>>2
-        uint32_t src_off16[4], src_nch[4], dst_off[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const uint32_t idx = i * 32 + lane, ch = idx >> 2, un = idx & 3;
-            src_off16[i] = __shfl_sync(0xffffffffu, off16, ch) + un;
-            src_nch[i] = __shfl_sync(0xffffffffu, done ? 0u : nchunks, ch);
-            dst_off[i] = ch * kChunk + ((un ^ ((ch >> 1) & 3)) << 4);
-        }
         auto issue = [&](uint32_t k) {
-            const uint32_t buf = stage_s + (k & 1) * kStageBytes;
+            const uint32_t dst = cp_dst + (k & 1) * kStageBytes;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + (((size_t)src_off16[i] + (size_t)k * 4) << 4);
-                cp_async16(buf + dst_off[i], src, k < src_nch[i] ? 16u : 0u);
+                const uint32_t ch = i * 8 + (lane >> 2);
+                const uint32_t o16 = __shfl_sync(0xffffffffu, off16, ch);
+                const uint32_t nch = __shfl_sync(0xffffffffu, nchunks, ch);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + (((size_t)o16 + (size_t)k * 4 + (lane & 3)) << 4);
+                cp_async16(dst + i * 8 * kRow, src, k < nch ? 16u : 0u);
             }
             cp_async_commit();
         };
@@ -379,6 +393,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             done = L.done != 0;
             pos = c.at;
             stop = c.stop;
+            warm = !done && L.kind == kPieceWarm;
             if (!done) {
                 s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
                 if (CP) {
@@ -387,6 +402,35 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 }
             }
         };
+        // the piece ended exactly where the fast path stands: the cheap, common transitions
+        // (warm-up -> head piece; end of the segment) without going through the exact scanner
+        auto piece_end_fast = [&]() -> bool {
+            if (warm) {
+                // arrived at the segment start in state s: that is the guess; scan the head piece from it
+                L.spec_state = __ldg(hot_img.hot2full + s / row_bytes);
+                L.kind = kPieceHead;
+                stop = min(L.hi_rel, c.limit);
+                c.stop = stop;
+                c.emit_from = 0;
+                cpd = 0;
+                warm = false;
+                return true;
+            }
+            if (stop == L.hi_rel) {
+                // end of the segment: write the summary
+                uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
+                const uint32_t nem = c.nemit;
+                dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + s / row_bytes), 0u,
+                                    L.kind == kPieceHead ? nem : L.head_count);
+                dst[1] = make_uint4(0u, CP ? cpd : 0u, 0u, 0u);
+                out.unit_counts[2 * L.seg] = 0;
+                out.unit_counts[2 * L.seg + 1] = nem;
+                L.done = 1;
+                done = true;
+                return true;
+            }
+            return false;
+        };
 
         __syncwarp();  // previous task's readers are done with both buffers
         if (kmax) issue(0);
@@ -394,17 +438,48 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             cp_async_wait_all();
             __syncwarp();
             if (k + 1 < kmax) issue(k + 1);
-            const uint8_t *buf = stage + (k & 1) * kStageBytes + lane * kChunk;
-            const uint32_t relk = rel0 + k * kChunk;
+            const uint8_t *row = stage + (k & 1) * kStageBytes + lane * kRow;
+            const uint32_t relk = k * kChunk;
+            if (!done && warm && pos == stop && pos == relk) piece_end_fast();  // the warm-up ended right at this chunk
+            if (!done && pos == relk && relk + kChunk <= stop) {
+                // ---- the whole 64-byte chunk in the fast path: one trap check for all of it ----
+                uint32_t t = s, hb = 0;
 #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                    t = fstep4<COLMODE>(t, w.x, ft);
+                    t = fstep4<COLMODE>(t, w.y, ft);
+                    t = fstep4<COLMODE>(t, w.z, ft);
+                    t = fstep4<COLMODE>(t, w.w, ft);
+                    if (CP) hb |= w.x | w.y | w.z | w.w;
+                }
+                n_groups += 4;
+                if (t != trap) {
+                    s = t;
+                    pos += kChunk;
+                    if (CP && (hb & 0x80808080u)) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                            cpd += cont_bytes(w.x) + cont_bytes(w.y) + cont_bytes(w.z) + cont_bytes(w.w);
+                        }
+                    }
+                    continue;
+                }
+                // something happened in these 64 bytes: redo them exactly, group by group below
+                n_traps++;
+                leave_fast(pos + 16);
+            }
+#pragma unroll 1
             for (int j = 0; j < 4; j++) {
                 const uint32_t g = relk + j * 16;
                 while (!done && g == pos) {
                     if (g + 16 > stop) {
-                        leave_fast(stop);  // the piece ends inside this group: finish it exactly, start the next one
+                        // the piece ends inside (or right at) this group
+                        if (!(pos == stop && piece_end_fast())) leave_fast(stop);
                         continue;
                     }
-                    const uint4 w = *reinterpret_cast<const uint4 *>(buf + ((j ^ my_swz) << 4));
+                    const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
                     uint32_t t = fstep4<COLMODE>(s, w.x, ft);
                     t = fstep4<COLMODE>(t, w.y, ft);
                     t = fstep4<COLMODE>(t, w.z, ft);
@@ -425,8 +500,10 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 }
             }
         }
-        // whatever is left (nothing, normally): exact to the end of the segment
-        while (!done) leave_fast(stop);
+        // the end of the segment (normally reached in the fast path, right at its last byte)
+        while (!done) {
+            if (!(pos == stop && piece_end_fast())) leave_fast(stop);
+        }
     }
     // how well the hot set fits the data: the host re-profiles when traps are frequent
 #pragma unroll
