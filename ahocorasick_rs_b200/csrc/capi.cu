@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) scan_plain_kernel(DevImage im, Batch B, S
         c.nemit = 0;
         c.cp_pos = 0;
         c.cp_cont = 0;
-        exact_scan<MODE, CP>(c, im, out, false, 0, 0, HotMap{nullptr, 0});
+        exact_scan<MODE, CP>(c, im, out, false, 0, HotMap{nullptr, 0});
         out.unit_counts[h] = c.nemit;
     }
 }

@@ -144,7 +144,9 @@ struct HotMap {
 // pass (which steps two scanners side by side), so both follow the same rules.
 template <int MODE, typename Emit>
 __device__ __forceinline__ void scan_byte(PieceCtx &c, const DevImage &im, uint32_t &s, uint32_t &at, Emit &&emit) {
-    const uint32_t col = __ldg(im.colmap + ld_u8(c.base + at));
+    const uint32_t b = ld_u8(c.base + at);
+    // kColRange: the column is arithmetic (one dependent load less per byte)
+    const uint32_t col = im.col_mode == kColRange ? min(b - im.col_lo, im.n_cols - 1) : (uint32_t)__ldg(im.colmap + b);
     const uint32_t e = __ldg(im.trans + (size_t)s * im.n_cols + col);
     s = e & kStateMask;
     at++;
@@ -186,18 +188,19 @@ __device__ __forceinline__ bool leftmost_flush(PieceCtx &c, uint32_t &s, uint32_
 // Runs the exact scanner from c.at until the piece is finished: at >= c.stop
 // with nothing pending (leftmost kinds run past c.stop while a match is
 // pending, never past c.limit) -- or, if stop_hot is set, as soon as
-//   at >= min_at, (at - phase) % 16 == 0, the state is hot and nothing is pending,
+//   at >= min_at, the state is hot and nothing is pending,
 // i.e. at a point where the staged fast path may take over again.
 template <int MODE, bool CP>
-__device__ __noinline__ void exact_scan(PieceCtx &c, const DevImage &im, const Sink &out, bool stop_hot,
-                                        uint32_t min_at, uint32_t phase, HotMap hm) {
+__device__ __noinline__ void exact_scan(PieceCtx &c, const DevImage &im_in, const Sink &out, bool stop_hot,
+                                        uint32_t min_at, HotMap hm) {
+    const DevImage im = im_in;  // private copy: the loop keeps the table pointers in registers
     uint32_t s = c.state, at = c.at;
+    const uint32_t stop = c.stop;
     auto emit = [&](uint32_t pid, uint32_t end) { report<CP>(c, im, out, pid, end); };
     for (;;) {
         if (leftmost_flush<MODE>(c, s, at, emit)) continue;
-        if (at >= c.stop && (MODE != kModeLeftmost || !c.have)) break;
-        if (stop_hot && at >= min_at && ((at - phase) & 15u) == 0 && (MODE != kModeLeftmost || !c.have) &&
-            (uint32_t)__ldg(hm.full2hot + s) < hm.hot_limit)
+        if (at >= stop && (MODE != kModeLeftmost || !c.have)) break;
+        if (stop_hot && at >= min_at && (MODE != kModeLeftmost || !c.have) && (uint32_t)__ldg(hm.full2hot + s) < hm.hot_limit)
             break;
         scan_byte<MODE>(c, im, s, at, emit);
     }

@@ -211,12 +211,12 @@ __device__ __noinline__ void advance_piece(PieceCtx &c, LaneSeg &L, const Batch 
 }
 
 // Runs the exact scanner until the lane is at a point where the fast path can take over
-// (16-byte aligned, hot state, nothing pending, inside a piece) or the segment is finished.
+// (hot state, nothing pending, inside a piece) or the segment is finished.
 template <int MODE, bool CP>
 __device__ __noinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im, const Batch &B, const Sink &out,
                                     SegInfo *seg_info, HotMap hm, uint32_t min_at) {
     for (;;) {
-        exact_scan<MODE, CP>(c, im, out, true, min_at, 0, hm);
+        exact_scan<MODE, CP>(c, im, out, true, min_at, hm);
         if (c.at >= c.stop && (MODE != kModeLeftmost || !c.have)) {
             advance_piece<MODE, CP>(c, L, B, out, seg_info);
             if (L.done) return;
@@ -343,14 +343,13 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             c.cp_pos = c.at;
             c.cp_cont = 0;
             warm = cont;
-            if ((c.at & 15u) == 0 && c.at + 16 <= c.stop) {
-                // starts on a 16-byte boundary in the root state (hot row 0): straight into the fast path
+            if (c.at < c.stop) {
+                // a piece always starts in the root state, which is hot row 0: straight into the fast path
                 pos = c.at;
                 stop = c.stop;
                 s = 0;
             } else {
-                // bytes before the first 16-byte boundary, pieces shorter than that, ...
-                settle<MODE, CP>(c, L, im, B, out, seg_info, hm, c.at);
+                settle<MODE, CP>(c, L, im, B, out, seg_info, hm, c.at);  // (cannot happen: segments are never empty here)
                 pos = c.at;
                 stop = c.stop;
                 warm = !L.done && L.kind == kPieceWarm;
@@ -466,38 +465,54 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                     }
                     continue;
                 }
-                // something happened in these 64 bytes: redo them exactly, group by group below
-                n_traps++;
-                leave_fast(pos + 16);
+                // something happened in these 64 bytes: go through them group by group below
+                // (s and pos are untouched); only the group it happened in is redone exactly
+                n_groups -= 4;
             }
 #pragma unroll 1
             for (int j = 0; j < 4; j++) {
                 const uint32_t g = relk + j * 16;
-                while (!done && g == pos) {
-                    if (g + 16 > stop) {
-                        // the piece ends inside (or right at) this group
-                        if (!(pos == stop && piece_end_fast())) leave_fast(stop);
-                        continue;
-                    }
+                if (done || pos < g || pos >= g + 16) continue;  // this lane is not inside this group
+                if (pos == g && g + 16 <= stop) {
+                    // a whole 16-byte group in the fast path
                     const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
                     uint32_t t = fstep4<COLMODE>(s, w.x, ft);
                     t = fstep4<COLMODE>(t, w.y, ft);
                     t = fstep4<COLMODE>(t, w.z, ft);
                     t = fstep4<COLMODE>(t, w.w, ft);
-                    n_groups++;
                     if (t != trap) {
+                        n_groups++;
                         s = t;
                         pos += 16;
                         if (CP) {
                             if ((w.x | w.y | w.z | w.w) & 0x80808080u)
                                 cpd += cont_bytes(w.x) + cont_bytes(w.y) + cont_bytes(w.z) + cont_bytes(w.w);
                         }
-                    } else {
-                        // something happened in these 16 bytes: redo them exactly
-                        n_traps++;
-                        leave_fast(pos + 16);
+                        continue;
                     }
                 }
+                // byte by byte through the hot table (bytes from the staged row): piece boundaries,
+                // unaligned positions, and the group something happens in -- the exact scanner only
+                // gets the byte that left the hot set
+                n_groups++;
+                bool trapped = false;
+                while (!done && pos >= g && pos < g + 16) {
+                    if (pos >= stop) {
+                        if (!(pos == stop && piece_end_fast())) leave_fast(stop);
+                        continue;
+                    }
+                    const uint32_t b = row[pos - relk];
+                    const uint32_t t = fstep<COLMODE>(s, b, ft);
+                    if (t != trap) {
+                        s = t;
+                        pos++;
+                        if (CP) cpd += (b & 0xC0u) == 0x80u;
+                    } else {
+                        trapped = true;
+                        leave_fast(pos + 1);
+                    }
+                }
+                n_traps += trapped;
             }
         }
         // the end of the segment (normally reached in the fast path, right at its last byte)

@@ -175,7 +175,7 @@ def leftmost_flush(c, mode, emit):
     return False
 
 
-def exact_scan(data, c, im, out, mode, cp, stop_hot=False, min_at=0, phase=0, hot_limit=0, f2h=None):
+def exact_scan(data, c, im, out, mode, cp, stop_hot=False, min_at=0, hot_limit=0, f2h=None):
     def emit(pid, end):
         report(data, c, im, out, cp, pid, end)
 
@@ -184,8 +184,7 @@ def exact_scan(data, c, im, out, mode, cp, stop_hot=False, min_at=0, phase=0, ho
             continue
         if c.at >= c.stop and (mode != 1 or not c.have):
             break
-        if (stop_hot and c.at >= min_at and ((c.at - phase) & 15) == 0 and (mode != 1 or not c.have)
-                and int(f2h[c.state]) < hot_limit):
+        if stop_hot and c.at >= min_at and (mode != 1 or not c.have) and int(f2h[c.state]) < hot_limit:
             break
         scan_byte(data, c, im, mode, emit)
 
@@ -276,7 +275,7 @@ def advance_piece(data, offsets, c, L, out, seg_info, cp):
 
 def settle(data, offsets, c, L, im, out, seg_info, mode, cp, H, f2h, min_at):
     while True:
-        exact_scan(data, c, im, out, mode, cp, True, min_at, 0, H, f2h)
+        exact_scan(data, c, im, out, mode, cp, True, min_at, H, f2h)
         if c.at >= c.stop and (mode != 1 or not c.have):
             advance_piece(data, offsets, c, L, out, seg_info, cp)
             if L.done:
@@ -323,13 +322,8 @@ def staged_segment(im, data, offsets, plan, seg, mode, cp, hotinfo, out, seg_inf
     c.hay_delta = (L.org - hs) & U32
     c.unit = 2 * seg + 1
     c.cp_pos, c.cp_cont = c.at, 0
-    settle(data, offsets, c, L, im, out, seg_info, mode, cp, H, f2h, c.at)
-    st = {"pos": c.at, "stop": c.stop, "s": 0, "cpd": 0}
-    if not L.done:
-        st["s"] = int(f2h[c.state])
-        if cp:
-            cp_catch_up(data, c, st["pos"])
-            st["cpd"] = c.cp_cont
+    assert c.at < c.stop
+    st = {"pos": c.at, "stop": c.stop, "s": 0, "cpd": 0, "warm": cont}   # root = hot row 0
 
     def leave_fast(min_at):
         c.state = int(h2f[st["s"]])
@@ -338,6 +332,7 @@ def staged_segment(im, data, offsets, plan, seg, mode, cp, hotinfo, out, seg_inf
             c.cp_pos, c.cp_cont = st["pos"], st["cpd"]
         settle(data, offsets, c, L, im, out, seg_info, mode, cp, H, f2h, min_at)
         st["pos"], st["stop"] = c.at, c.stop
+        st["warm"] = (not L.done) and L.kind == WARM
         if not L.done:
             st["s"] = int(f2h[c.state])
             assert st["s"] < H, "exact_scan must hand back a hot state"
@@ -345,31 +340,85 @@ def staged_segment(im, data, offsets, plan, seg, mode, cp, hotinfo, out, seg_inf
                 cp_catch_up(data, c, st["pos"])
                 st["cpd"] = c.cp_cont
 
+    def piece_end_fast():
+        if st["warm"]:
+            L.spec_state = int(h2f[st["s"]])
+            L.kind = HEAD
+            st["stop"] = min(L.hi_rel, c.limit)
+            c.stop = st["stop"]
+            c.emit_from = 0
+            st["cpd"] = 0
+            st["warm"] = False
+            return True
+        if st["stop"] == L.hi_rel:
+            seg_info[L.seg] = dict(spec_state=L.spec_state, end_state=int(h2f[st["s"]]), end_over=0,
+                                   head_count=c.nemit if L.kind == HEAD else L.head_count, drop=0,
+                                   cont_tail=st["cpd"] if cp else 0)
+            out.unit_counts[2 * L.seg] = 0
+            out.unit_counts[2 * L.seg + 1] = c.nemit
+            L.done = True
+            return True
+        return False
+
+    def fast_bytes(pos, n):
+        """n bytes from pos through the hot table; -> (state, number of bytes before the trap or n)"""
+        t = st["s"]
+        grp = data[c.base + pos: c.base + pos + n]
+        for b in grp:
+            t = int(hot[t, im.col(int(b))])
+        return t, grp
+
     for k in range(nchunks):
-        for j in range(4):
-            g = 64 * k + 16 * j
-            while not L.done and g == st["pos"]:
-                if g + 16 > st["stop"]:
-                    leave_fast(st["stop"])
-                    continue
-                t = st["s"]
-                pos = st["pos"]
-                grp = data[c.base + pos: c.base + pos + 16]
-                for b in grp:
-                    t = int(hot[t, im.col(int(b))])
+        relk = 64 * k
+        if not L.done and st["warm"] and st["pos"] == st["stop"] and st["pos"] == relk:
+            piece_end_fast()
+        if not L.done and st["pos"] == relk and relk + 64 <= st["stop"]:
+            t, grp = fast_bytes(relk, 64)
+            if t != H:
+                st["s"] = t
+                st["pos"] += 64
+                if cp:
+                    st["cpd"] += int(np.count_nonzero((grp & 0xC0) == 0x80))
                 if stats is not None:
-                    stats["groups"] = stats.get("groups", 0) + 1
+                    stats["groups"] = stats.get("groups", 0) + 4
+                continue
+        for j in range(4):
+            g = relk + 16 * j
+            if L.done or st["pos"] < g or st["pos"] >= g + 16:
+                continue
+            if st["pos"] == g and g + 16 <= st["stop"]:
+                t, grp = fast_bytes(g, 16)
                 if t != H:
                     st["s"] = t
-                    st["pos"] = pos + 16
+                    st["pos"] += 16
                     if cp:
                         st["cpd"] += int(np.count_nonzero((grp & 0xC0) == 0x80))
-                else:
                     if stats is not None:
-                        stats["traps"] = stats.get("traps", 0) + 1
-                    leave_fast(pos + 16)
+                        stats["groups"] = stats.get("groups", 0) + 1
+                    continue
+            if stats is not None:
+                stats["groups"] = stats.get("groups", 0) + 1
+            trapped = False
+            while not L.done and g <= st["pos"] < g + 16:
+                if st["pos"] >= st["stop"]:
+                    if not (st["pos"] == st["stop"] and piece_end_fast()):
+                        leave_fast(st["stop"])
+                    continue
+                b = int(data[c.base + st["pos"]])
+                t = int(hot[st["s"], im.col(b)])
+                if t != H:
+                    st["s"] = t
+                    st["pos"] += 1
+                    if cp:
+                        st["cpd"] += (b & 0xC0) == 0x80
+                else:
+                    trapped = True
+                    leave_fast(st["pos"] + 1)
+            if trapped and stats is not None:
+                stats["traps"] = stats.get("traps", 0) + 1
     while not L.done:
-        leave_fast(st["stop"])
+        if not (st["pos"] == st["stop"] and piece_end_fast()):
+            leave_fast(st["stop"])
 
 
 # ------------------------------------------------------------------ repair.cuh
