@@ -456,7 +456,7 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
     const uint32_t row_bytes = im.n_cols * 2;
-    const uint32_t stage_bytes = (uint32_t)warps * 2 * kStageBytes;
+    const uint32_t stage_bytes = (uint32_t)warps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
     uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row

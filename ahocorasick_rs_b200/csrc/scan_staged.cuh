@@ -15,6 +15,7 @@
 //        (cp.async.bulk + mbarrier) when the whole hot image fits.
 //   [ column map : 256 B ]  (kColClass only)
 //   [ mbarrier ]
+//   [ copy metadata : per warp 32 x (first 16-byte unit, number of chunks) ]
 //   [ staging : per warp, 2 buffers x 32 lanes x 80 B ]  lane l's 64-byte
 //        chunk at a pitch of 80 bytes: consecutive lanes start 5 sixteen-byte
 //        units apart, so the per-lane LDS.128 reads of a quarter warp hit 8
@@ -45,6 +46,7 @@ constexpr int kChunk = 64;                // bytes per lane per stage
 constexpr int kRow = kChunk + 16;         // a lane's row in the staging buffer: 80-byte pitch = conflict-free LDS.128 without a swizzle
 constexpr int kStageBytes = 32 * kRow;    // per warp per buffer
 constexpr int kStageOffset = 256 + 128;   // column map + mbarrier slot, after the hot table
+constexpr int kMetaBytes = 32 * 8;        // per warp: (first 16-byte unit, chunk count) of each lane, read by the copy issue
 
 struct FastTab {
     const uint8_t *hot;   // shared: the table, addressed in bytes
@@ -272,7 +274,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     uint32_t n_groups = 0, n_traps = 0;
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint8_t *stage = stage_all + (size_t)warp * 2 * kStageBytes;
+    uint2 *meta = reinterpret_cast<uint2 *>(stage_all + (size_t)warp * kMetaBytes);
+    uint8_t *stage = stage_all + (size_t)(blockDim.x >> 5) * kMetaBytes + (size_t)warp * 2 * kStageBytes;
     const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
     const uintptr_t gbase = reinterpret_cast<uintptr_t>(B.bytes + P.origin);  // 64-byte aligned by construction of the plan
     // copy instruction i of a stage moves 16-byte unit (lane & 3) of lane (i * 8 + lane / 4)
@@ -363,20 +366,24 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             }
         }
         bool done = L.done != 0;
-        uint32_t kmax = done ? 0u : nchunks;
+        if (done) nchunks = 0;
+        uint32_t kmax = nchunks;
 #pragma unroll
         for (int d = 16; d; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
-        if (done) nchunks = 0;
+        // where each lane's bytes are: read back by whichever lane copies them (no shuffles in the loop:
+        // the compiler cannot prove the warp converged there and would emit a slow collective path)
+        __syncwarp();  // the previous task no longer reads meta / the staging buffers
+        meta[lane] = make_uint2(off16, nchunks);
+        __syncwarp();
+        if (!done) n_groups += (L.hi_rel - c.at) >> 4;
 
         auto issue = [&](uint32_t k) {
             const uint32_t dst = cp_dst + (k & 1) * kStageBytes;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const uint32_t ch = i * 8 + (lane >> 2);
-                const uint32_t o16 = __shfl_sync(0xffffffffu, off16, ch);
-                const uint32_t nch = __shfl_sync(0xffffffffu, nchunks, ch);
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + (((size_t)o16 + (size_t)k * 4 + (lane & 3)) << 4);
-                cp_async16(dst + i * 8 * kRow, src, k < nch ? 16u : 0u);
+                const uint2 m = meta[i * 8 + (lane >> 2)];
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + (((size_t)m.x + (size_t)k * 4 + (lane & 3)) << 4);
+                cp_async16(dst + i * 8 * kRow, src, k < m.y ? 16u : 0u);
             }
             cp_async_commit();
         };
@@ -431,7 +438,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             return false;
         };
 
-        __syncwarp();  // previous task's readers are done with both buffers
         if (kmax) issue(0);
         for (uint32_t k = 0; k < kmax; k++) {
             cp_async_wait_all();
@@ -452,22 +458,20 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                     t = fstep4<COLMODE>(t, w.w, ft);
                     if (CP) hb |= w.x | w.y | w.z | w.w;
                 }
-                n_groups += 4;
                 if (t != trap) {
                     s = t;
                     pos += kChunk;
                     if (CP && (hb & 0x80808080u)) {
+                        // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
+                        // continuation bytes from the staged row again (volatile: do not keep 16 words live for this)
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
-                            cpd += cont_bytes(w.x) + cont_bytes(w.y) + cont_bytes(w.z) + cont_bytes(w.w);
-                        }
+                        for (int j = 0; j < 16; j++)
+                            cpd += cont_bytes(*reinterpret_cast<const volatile uint32_t *>(row + j * 4));
                     }
                     continue;
                 }
                 // something happened in these 64 bytes: go through them group by group below
                 // (s and pos are untouched); only the group it happened in is redone exactly
-                n_groups -= 4;
             }
 #pragma unroll 1
             for (int j = 0; j < 4; j++) {
@@ -481,7 +485,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                     t = fstep4<COLMODE>(t, w.z, ft);
                     t = fstep4<COLMODE>(t, w.w, ft);
                     if (t != trap) {
-                        n_groups++;
                         s = t;
                         pos += 16;
                         if (CP) {
@@ -494,7 +497,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // byte by byte through the hot table (bytes from the staged row): piece boundaries,
                 // unaligned positions, and the group something happens in -- the exact scanner only
                 // gets the byte that left the hot set
-                n_groups++;
                 bool trapped = false;
                 while (!done && pos >= g && pos < g + 16) {
                     if (pos >= stop) {
