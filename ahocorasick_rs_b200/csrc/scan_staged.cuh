@@ -38,6 +38,8 @@
 // touches 8 x 64 contiguous bytes.  Chunk k+1 is in flight while chunk k is
 // scanned (the scan of a chunk takes longer than an HBM round trip).
 #pragma once
+#include <type_traits>
+
 #include "scan_core.cuh"
 
 namespace acb {
@@ -377,13 +379,14 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         __syncwarp();
         if (!done) n_groups += (L.hi_rel - c.at) >> 4;
 
-        auto issue = [&](uint32_t k) {
-            const uint32_t dst = cp_dst + (k & 1) * kStageBytes;
+        // stage chunk k into buffer BUF (compile-time: every shared-memory address below is base + immediate)
+        auto issue = [&](auto buf_tag, uint32_t k) {
+            constexpr uint32_t BUF = decltype(buf_tag)::value;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const uint2 m = meta[i * 8 + (lane >> 2)];
-                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + (((size_t)m.x + (size_t)k * 4 + (lane & 3)) << 4);
-                cp_async16(dst + i * 8 * kRow, src, k < m.y ? 16u : 0u);
+                const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + ((size_t)(m.x + k * 4 + (lane & 3)) << 4);
+                cp_async16(cp_dst + BUF * kStageBytes + i * 8 * kRow, src, k < m.y ? 16u : 0u);
             }
             cp_async_commit();
         };
@@ -438,12 +441,15 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             return false;
         };
 
-        if (kmax) issue(0);
-        for (uint32_t k = 0; k < kmax; k++) {
+        using Buf0 = std::integral_constant<uint32_t, 0>;
+        using Buf1 = std::integral_constant<uint32_t, 1>;
+        const uint8_t *row0 = stage + lane * kRow;
+        auto body = [&](auto buf_tag, uint32_t k) {
+            constexpr uint32_t BUF = decltype(buf_tag)::value;
             cp_async_wait_all();
             __syncwarp();
-            if (k + 1 < kmax) issue(k + 1);
-            const uint8_t *row = stage + (k & 1) * kStageBytes + lane * kRow;
+            if (k + 1 < kmax) issue(std::integral_constant<uint32_t, 1 - BUF>{}, k + 1);
+            const uint8_t *row = row0 + BUF * kStageBytes;
             const uint32_t relk = k * kChunk;
             if (!done && warm && pos == stop && pos == relk) piece_end_fast();  // the warm-up ended right at this chunk
             if (!done && pos == relk && relk + kChunk <= stop) {
@@ -468,7 +474,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                         for (int j = 0; j < 16; j++)
                             cpd += cont_bytes(*reinterpret_cast<const volatile uint32_t *>(row + j * 4));
                     }
-                    continue;
+                    return;
                 }
                 // something happened in these 64 bytes: go through them group by group below
                 // (s and pos are untouched); only the group it happened in is redone exactly
@@ -516,6 +522,11 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 }
                 n_traps += trapped;
             }
+        };
+        if (kmax) issue(Buf0{}, 0);
+        for (uint32_t k = 0; k < kmax; k += 2) {
+            body(Buf0{}, k);
+            if (k + 1 < kmax) body(Buf1{}, k + 1);
         }
         // the end of the segment (normally reached in the fast path, right at its last byte)
         while (!done) {
