@@ -30,7 +30,11 @@ class Workspace(C.Structure):
 
 
 class Tuning(C.Structure):
-    _fields_ = [("kernel", C.c_int), ("hot_rows", C.c_int), ("segment_bytes", C.c_int), ("reserved", C.c_int)]
+    _fields_ = [("kernel", C.c_int), ("hot_rows", C.c_int), ("segment_bytes", C.c_int), ("table", C.c_int)]
+
+
+class HotDesc(C.Structure):
+    _fields_ = [("rows", C.c_uint32), ("rows128", C.c_uint32), ("visited", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 _lib = None
@@ -70,7 +74,8 @@ def lib():
         L.acb_hot_build.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
         L.acb_hot_rows.restype = C.c_uint32
         L.acb_hot_rows.argtypes = [C.c_void_p]
-        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_int64,
+        L.acb_hot_describe.argtypes = [C.c_void_p, C.POINTER(HotDesc)]
+        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HotDesc), C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_uint64, C.c_int, C.c_int, C.POINTER(Plan), C.POINTER(Workspace), C.c_void_p]
         _lib = L
     return _lib
@@ -85,5 +90,5 @@ EXPORTS = [
     "acb_num_columns", "acb_max_pattern_len", "acb_min_pattern_len", "acb_match_kind", "acb_image_bytes",
     "acb_image_write", "acb_plan_scan", "acb_scan_batch",
     "acb_launch_count", "acb_set_tuning", "acb_timing_enable", "acb_timing_read",
-    "acb_profile", "acb_hot_bytes", "acb_hot_build", "acb_hot_rows",
+    "acb_profile", "acb_hot_bytes", "acb_hot_build", "acb_hot_rows", "acb_hot_describe",
 ]

@@ -300,12 +300,24 @@ static uint32_t hot_rows_for(const Automaton &a, uint32_t max_rows) {
     return H;
 }
 
+// ASCII table: available when every byte >= 0x7f falls in the "no pattern uses it" column
+static uint32_t ascii_rows_for(const Automaton &a, uint32_t H) {
+    const uint8_t *colmap = a.image.data() + a.hdr.off_colmap;
+    const uint8_t other = colmap[255];
+    for (uint32_t b = 127; b < 256; b++)
+        if (colmap[b] != other) return 0;
+    // column `other` must really be the shared one: no trie edge uses it
+    if (a.hdr.col_mode == kColRange ? other != a.hdr.n_cols - 1 : other != 0) return 0;
+    return H < 255 ? H : 255;  // the trap row starts at 255 * 256 < 64 KiB
+}
+
 uint64_t hot_image_bytes(const Automaton &a, uint32_t max_rows) {
     const uint32_t H = hot_rows_for(a, max_rows);
     uint64_t off = align16(sizeof(HotHeader));
     off = align16(off + uint64_t(H + 1) * a.hdr.n_cols * 2);
     off = align16(off + uint64_t(H + 1) * 4);
     off = align16(off + uint64_t(a.hdr.n_states) * 2);
+    off = align16(off + uint64_t(ascii_rows_for(a, H) + 1) * kAsciiCols * 2);
     return off;
 }
 
@@ -325,9 +337,12 @@ void build_hot_image(const Automaton &a, const uint32_t *visits, uint32_t max_ro
     off = align16(off + uint64_t(H + 1) * 4);
     hh.off_full2hot = off;
     off = align16(off + uint64_t(n_states) * 2);
+    const uint32_t H128 = ascii_rows_for(a, H);
+    hh.n_rows128 = H128;
+    hh.off_table128 = off;
+    off = align16(off + uint64_t(H128 + 1) * kAsciiCols * 2);
     hh.total_bytes = off;
     std::memset(dst, 0, off);
-    std::memcpy(dst, &hh, sizeof(hh));
     uint16_t *table = reinterpret_cast<uint16_t *>(dst + hh.off_table);
     uint32_t *hot2full = reinterpret_cast<uint32_t *>(dst + hh.off_hot2full);
     uint16_t *full2hot = reinterpret_cast<uint16_t *>(dst + hh.off_full2hot);
@@ -342,10 +357,12 @@ void build_hot_image(const Automaton &a, const uint32_t *visits, uint32_t max_ro
         }
     };
     take(kRoot);
+    uint32_t n_visited = 1;
     if (visits) {
         std::vector<uint32_t> seen;
         for (uint32_t s = kRoot; s < n_states; s++)
             if (visits[s]) seen.push_back(s);
+        n_visited = static_cast<uint32_t>(seen.size()) + (visits[kRoot] ? 0 : 1);
         const size_t keep = std::min<size_t>(seen.size(), H);
         std::partial_sort(seen.begin(), seen.begin() + keep, seen.end(), [&](uint32_t x, uint32_t y) {
             return visits[x] != visits[y] ? visits[x] > visits[y] : x < y;
@@ -369,6 +386,25 @@ void build_hot_image(const Automaton &a, const uint32_t *visits, uint32_t max_ro
     }
     for (uint32_t c = 0; c < n_cols; c++) table[uint64_t(H) * n_cols + c] = static_cast<uint16_t>(H * row_bytes);
     hot2full[H] = kDead;
+
+    if (H128) {
+        // the same rows, indexed by the raw byte (bytes >= 128 are clamped to column 127 by the scan,
+        // which is the "no pattern uses it" column by construction)
+        uint16_t *t128 = reinterpret_cast<uint16_t *>(dst + hh.off_table128);
+        const uint8_t *colmap = a.image.data() + ih.off_colmap;
+        for (uint32_t h = 0; h < H128; h++) {
+            const uint32_t *row = T + uint64_t(hot2full[h]) * n_cols;
+            for (uint32_t b = 0; b < kAsciiCols; b++) {
+                const uint32_t e = row[colmap[b]], t = e & kStateMask;
+                uint32_t v = H128;
+                if (!(e & kMatchFlag) && t != kDead && full2hot[t] < H128) v = full2hot[t];
+                t128[uint64_t(h) * kAsciiCols + b] = static_cast<uint16_t>(v * kAsciiCols * 2);
+            }
+        }
+        for (uint32_t b = 0; b < kAsciiCols; b++) t128[uint64_t(H128) * kAsciiCols + b] = static_cast<uint16_t>(H128 * kAsciiCols * 2);
+    }
+    hh.n_visited = n_visited > H ? H : n_visited;
+    std::memcpy(dst, &hh, sizeof(hh));
 }
 
 }  // namespace acb

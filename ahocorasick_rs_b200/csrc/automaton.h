@@ -61,7 +61,14 @@ struct HotHeader {
     uint64_t off_hot2full;  // u32[H + 1]
     uint64_t off_full2hot;  // u16[n_states]; 0xffff = not hot
     uint64_t total_bytes;
+    // ASCII variant of the table (only when no pattern uses a byte >= 0x7f): the first n_rows128 hot
+    // rows again, 128 entries wide and indexed by the raw byte, so the scan needs no byte -> column
+    // arithmetic at all on text without high bytes.  0 rows = not available.
+    uint32_t n_rows128;
+    uint32_t n_visited;     // rows that the profile actually saw (the rest is filler)
+    uint64_t off_table128;  // u16[(n_rows128 + 1) * 128]; entries are row byte offsets (index * 256)
 };
+constexpr uint32_t kAsciiCols = 128;
 constexpr uint32_t kHotMagic = 0x31424341u;  // "ACB1"
 constexpr uint16_t kNotHot = 0xffffu;
 

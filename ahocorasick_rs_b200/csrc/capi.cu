@@ -245,7 +245,7 @@ struct acb_automaton {
 
 static thread_local std::string g_err;
 static unsigned long long g_launches = 0;
-static acb_tuning g_tuning = {0, 0, 0, 0};
+static acb_tuning g_tuning = {0, 0, 0, 0};  // kernel, hot_rows, segment_bytes, table
 
 // optional device timing of the dominant (scan) kernel, for bench.py's roofline
 static bool g_timing = false;
@@ -345,6 +345,16 @@ uint32_t acb_hot_rows(const void *host_hot) {
     return (h && h->magic == kHotMagic) ? h->n_rows : 0;
 }
 
+int acb_hot_describe(const void *host_hot, acb_hot_desc *desc) {
+    const HotHeader *h = static_cast<const HotHeader *>(host_hot);
+    if (!h || !desc || h->magic != kHotMagic) return fail(ACB_EINVAL, "not a hot image");
+    desc->rows = h->n_rows;
+    desc->rows128 = h->n_rows128;
+    desc->visited = h->n_visited;
+    desc->reserved = 0;
+    return ACB_OK;
+}
+
 int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_bytes, uint64_t n_haystacks, acb_plan *plan) {
     if (!a || !plan) return fail(ACB_EINVAL, "null argument");
     const uint32_t L = a->impl->hdr.max_pat_len;
@@ -418,9 +428,11 @@ DevImage make_view(const ImageHeader &h, const void *dev_image) {
 
 // dev_hot points at a device copy of a hot image; hot_rows is its row count (the
 // host knows it: acb_hot_rows on the host copy), because the header lives on the device
-int make_hot_view(const acb_automaton *a, const void *dev_hot, uint32_t hot_rows, DevHot &v) {
+int make_hot_view(const acb_automaton *a, const void *dev_hot, const acb_hot_desc &desc, DevHot &v) {
     const ImageHeader &ih = a->impl->hdr;
-    if (hot_rows < 1 || (uint64_t)hot_rows * ih.n_cols * 2 > 65535) return fail(ACB_EINVAL, "bad hot image row count");
+    const uint32_t hot_rows = desc.rows;
+    if (hot_rows < 1 || (uint64_t)hot_rows * ih.n_cols * 2 > 65535 || desc.rows128 > 255)
+        return fail(ACB_EINVAL, "bad hot image description");
     auto align16 = [](uint64_t x) { return (x + 15) & ~uint64_t(15); };
     const uint8_t *b = static_cast<const uint8_t *>(dev_hot);
     uint64_t off = align16(sizeof(HotHeader));
@@ -430,6 +442,9 @@ int make_hot_view(const acb_automaton *a, const void *dev_hot, uint32_t hot_rows
     off = align16(off + uint64_t(hot_rows + 1) * 4);
     v.full2hot = reinterpret_cast<const uint16_t *>(b + off);
     v.n_rows = hot_rows;
+    off = align16(off + uint64_t(ih.n_states) * 2);
+    v.table128 = reinterpret_cast<const uint16_t *>(b + off);
+    v.n_rows128 = desc.rows128;
     return ACB_OK;
 }
 
@@ -455,13 +470,14 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     int warps = (int)((tasks + ctas - 1) / ctas);
     if (warps < 4) warps = 4;
     if (warps > 32) warps = 32;
-    const uint32_t row_bytes = im.n_cols * 2;
+    const uint32_t row_bytes = COLMODE == kColAscii ? kAsciiCols * 2 : im.n_cols * 2;
     const uint32_t stage_bytes = (uint32_t)warps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
     uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
     uint32_t H = rows - 1;
-    if (H > hot.n_rows) H = hot.n_rows;
+    const uint32_t have = COLMODE == kColAscii ? hot.n_rows128 : hot.n_rows;
+    if (H > have) H = have;
     if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
     if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
     const uint32_t hot_bytes = (((H + 1) * row_bytes) + 127u) & ~127u;
@@ -472,10 +488,19 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     return ACB_OK;
 }
 
+// how many 128-wide rows fit next to the staging buffers of a full CTA
+uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
+    const uint32_t stage_bytes = 32u * (2 * kStageBytes + kMetaBytes);
+    const uint32_t budget = (uint32_t)d.max_smem_optin;
+    if (budget < stage_bytes + kStageOffset + 128 + 2 * kAsciiCols * 2) return 0;
+    return (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2) - 1;
+}
+
 template <int MODE, bool CP>
 int launch_staged_cols(const ImageHeader &h, const DevImage &im, const DevHot &hot, const Batch &B, const SegPlan &P, const Sink &out,
                        SegInfo *seg_info, const DeviceInfo &d, unsigned int *task_counter, unsigned long long *trap_stats,
-                       cudaStream_t st) {
+                       cudaStream_t st, bool ascii) {
+    if (ascii) return launch_staged<MODE, CP, kColAscii>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
     if (h.col_mode == kColRange)
         return launch_staged<MODE, CP, kColRange>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
     return launch_staged<MODE, CP, kColClass>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
@@ -523,7 +548,7 @@ int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *de
     return ACB_OK;
 }
 
-int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
+int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, const acb_hot_desc *hot_desc,
                    const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
                    int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream) {
     if (!a || !dev_image || !dev_offsets || n_haystacks < 0 || !plan) return fail(ACB_EINVAL, "bad argument");
@@ -574,10 +599,12 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
 
     int kernel = g_tuning.kernel;
     if (kernel == 0) kernel = 2;
-    if (!dev_hot) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
+    if (!dev_hot || !hot_desc) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
     const bool segments = kernel == 2;
     SegPlan P{};
     uint64_t n_units = (uint64_t)n_haystacks;
+    bool totals_flag_ascii = false;
+    (void)totals_flag_ascii;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (g_timing) {
@@ -591,7 +618,12 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
                              : (cp ? FN<kModeOverlap, true>(__VA_ARGS__) : FN<kModeOverlap, false>(__VA_ARGS__)))
     if (segments) {
         DevHot hot;
-        if ((rc = make_hot_view(a, dev_hot, hot_rows, hot))) return rc;
+        if ((rc = make_hot_view(a, dev_hot, *hot_desc, hot))) return rc;
+        // the byte-indexed table is used when it exists and every row the profile saw fits on chip
+        uint32_t fit128 = ascii_rows_that_fit(d);
+        if (fit128 > hot.n_rows128) fit128 = hot.n_rows128;
+        if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < fit128) fit128 = (uint32_t)g_tuning.hot_rows;
+        const bool ascii = g_tuning.table != 1 && fit128 > 0 && (g_tuning.table == 2 || fit128 >= hot_desc->visited);
         // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
         // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
         P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);
@@ -601,7 +633,8 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         P.lane_stride = plan->lane_stride;
         P.avg_len = n_haystacks > 0 ? total_bytes / (uint64_t)n_haystacks : 0;
         n_units = 2 * plan->n_segments;
-        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st);
+        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st, ascii);
+        totals_flag_ascii = ascii;
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());
         if (ev1) {

@@ -56,19 +56,35 @@ struct FastTab {
     uint32_t lo, maxc;
 };
 
-template <int COLMODE>
+constexpr int kColAscii = 2;  // hot table indexed by the raw byte (128 entries per row); bytes >= 128 clamp to 127
+
+template <int COLMODE, bool CLAMP = true>
 __device__ __forceinline__ uint32_t fstep(uint32_t s, uint32_t b, const FastTab &f) {
-    const uint32_t col = (COLMODE == kColRange) ? min(b - f.lo, f.maxc) : (uint32_t)f.cmap[b];
+    uint32_t col;
+    if (COLMODE == kColRange)
+        col = min(b - f.lo, f.maxc);
+    else if (COLMODE == kColClass)
+        col = (uint32_t)f.cmap[b];
+    else
+        col = CLAMP ? min(b, 127u) : b;
     return *reinterpret_cast<const uint16_t *>(f.hot + s + (col << 1));
 }
 
-template <int COLMODE>
+template <int COLMODE, bool CLAMP = true>
 __device__ __forceinline__ uint32_t fstep4(uint32_t s, uint32_t w, const FastTab &f) {
-    s = fstep<COLMODE>(s, __byte_perm(w, 0, 0x4440), f);
-    s = fstep<COLMODE>(s, __byte_perm(w, 0, 0x4441), f);
-    s = fstep<COLMODE>(s, __byte_perm(w, 0, 0x4442), f);
-    s = fstep<COLMODE>(s, __byte_perm(w, 0, 0x4443), f);
+    s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4440), f);
+    s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4441), f);
+    s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4442), f);
+    s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4443), f);
     return s;
+}
+
+__device__ __forceinline__ uint4 lds128_volatile(const uint8_t *p) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return v;
 }
 
 // continuation bytes (10xxxxxx) in a word
@@ -113,6 +129,8 @@ struct DevHot {
     const uint32_t *hot2full;
     const uint16_t *full2hot;
     uint32_t n_rows;
+    const uint16_t *table128;  // kColAscii
+    uint32_t n_rows128;
 };
 
 // What a lane knows about its segment besides the scanner state (kept out of
@@ -239,18 +257,20 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     uint8_t *hot = smem;
     uint8_t *cmap = smem + hot_bytes;                     // 256 B
     uint8_t *stage_all = smem + hot_bytes + kStageOffset;  // 128-aligned by construction
-    const uint32_t row_bytes = im.n_cols * 2;
+    const uint32_t row_entries = COLMODE == kColAscii ? kAsciiCols : im.n_cols;
+    const uint32_t row_bytes = row_entries * 2;
     const uint32_t trap = H * row_bytes;
+    const uint16_t *src_table = COLMODE == kColAscii ? hot_img.table128 : hot_img.table;
 
     // ---- prologue: the hot table (L2 resident) ------------------------------------------
-    if (H == hot_img.n_rows) {
+    if (H == (COLMODE == kColAscii ? hot_img.n_rows128 : hot_img.n_rows)) {
         // the whole image fits: one TMA bulk copy, completion on an mbarrier
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem + hot_bytes + 256);
         const uint32_t bytes = ((H + 1) * row_bytes + 15u) & ~15u;
         if (threadIdx.x == 0) {
             mbar_init(bar, 1);
             mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(hot), hot_img.table, bytes, bar);
+            tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(hot), src_table, bytes, bar);
         }
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
         __syncthreads();  // the barrier is initialised before anyone polls it
@@ -258,9 +278,15 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     } else {
         // a prefix of the image (rows are hottest-first): entries beyond it become the trap
         uint16_t *h16 = reinterpret_cast<uint16_t *>(hot);
-        const uint32_t n = H * im.n_cols;
-        for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) h16[i] = (uint16_t)min((uint32_t)__ldg(hot_img.table + i), trap);
-        for (uint32_t i = threadIdx.x; i < im.n_cols; i += blockDim.x) h16[n + i] = (uint16_t)trap;
+        const uint32_t n = H * row_entries;
+        const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src_table);  // 16-byte aligned in the image
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(hot);
+        for (uint32_t i = threadIdx.x; i < n / 2; i += blockDim.x) {
+            const uint32_t v = __ldg(src32 + i);
+            dst32[i] = min(v & 0xffffu, trap) | (min(v >> 16, trap) << 16);
+        }
+        if ((n & 1u) && threadIdx.x == 0) h16[n - 1] = (uint16_t)min((uint32_t)__ldg(src_table + n - 1), trap);
+        for (uint32_t i = threadIdx.x; i < row_entries; i += blockDim.x) h16[n + i] = (uint16_t)trap;
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
     }
     __syncthreads();
@@ -441,44 +467,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             return false;
         };
 
-        using Buf0 = std::integral_constant<uint32_t, 0>;
-        using Buf1 = std::integral_constant<uint32_t, 1>;
-        const uint8_t *row0 = stage + lane * kRow;
-        auto body = [&](auto buf_tag, uint32_t k) {
-            constexpr uint32_t BUF = decltype(buf_tag)::value;
-            cp_async_wait_all();
-            __syncwarp();
-            if (k + 1 < kmax) issue(std::integral_constant<uint32_t, 1 - BUF>{}, k + 1);
-            const uint8_t *row = row0 + BUF * kStageBytes;
-            const uint32_t relk = k * kChunk;
-            if (!done && warm && pos == stop && pos == relk) piece_end_fast();  // the warm-up ended right at this chunk
-            if (!done && pos == relk && relk + kChunk <= stop) {
-                // ---- the whole 64-byte chunk in the fast path: one trap check for all of it ----
-                uint32_t t = s, hb = 0;
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
-                    t = fstep4<COLMODE>(t, w.x, ft);
-                    t = fstep4<COLMODE>(t, w.y, ft);
-                    t = fstep4<COLMODE>(t, w.z, ft);
-                    t = fstep4<COLMODE>(t, w.w, ft);
-                    if (CP) hb |= w.x | w.y | w.z | w.w;
-                }
-                if (t != trap) {
-                    s = t;
-                    pos += kChunk;
-                    if (CP && (hb & 0x80808080u)) {
-                        // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
-                        // continuation bytes from the staged row again (volatile: do not keep 16 words live for this)
-#pragma unroll
-                        for (int j = 0; j < 16; j++)
-                            cpd += cont_bytes(*reinterpret_cast<const volatile uint32_t *>(row + j * 4));
-                    }
-                    return;
-                }
-                // something happened in these 64 bytes: go through them group by group below
-                // (s and pos are untouched); only the group it happened in is redone exactly
-            }
+        // everything that is not a clean whole chunk: 16-byte groups, then single bytes (one instance of this code)
+        auto generic = [&](uint32_t relk, const uint8_t *row) {
 #pragma unroll 1
             for (int j = 0; j < 4; j++) {
                 const uint32_t g = relk + j * 16;
@@ -522,6 +512,72 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 }
                 n_traps += trapped;
             }
+        };
+        using Buf0 = std::integral_constant<uint32_t, 0>;
+        using Buf1 = std::integral_constant<uint32_t, 1>;
+        const uint8_t *row0 = stage + lane * kRow;
+        auto body = [&](auto buf_tag, uint32_t k) {
+            constexpr uint32_t BUF = decltype(buf_tag)::value;
+            cp_async_wait_all();
+            __syncwarp();
+            if (k + 1 < kmax) issue(std::integral_constant<uint32_t, 1 - BUF>{}, k + 1);
+            const uint8_t *row = row0 + BUF * kStageBytes;
+            const uint32_t relk = k * kChunk;
+            if (!done && warm && pos == stop && pos == relk) piece_end_fast();  // the warm-up ended right at this chunk
+            if (!done && pos == relk && relk + kChunk <= stop) {
+                // ---- the whole 64-byte chunk in the fast path: one trap check for all of it ----
+                uint32_t t = s, hb = 0;
+                if (COLMODE == kColAscii) {
+                    // raw-byte indexing is only valid without high bytes: look first (separate loads, so
+                    // that the 16 words are not kept in registers across the scan)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 w = lds128_volatile(row + j * 16);
+                        hb |= w.x | w.y | w.z | w.w;
+                    }
+                    if (!(hb & 0x80808080u)) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                            t = fstep4<COLMODE, false>(t, w.x, ft);
+                            t = fstep4<COLMODE, false>(t, w.y, ft);
+                            t = fstep4<COLMODE, false>(t, w.z, ft);
+                            t = fstep4<COLMODE, false>(t, w.w, ft);
+                        }
+                        if (t != trap) {
+                            s = t;
+                            pos += kChunk;
+                            return;
+                        }
+                    }
+                    // high bytes or an event: group by group below
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                        t = fstep4<COLMODE>(t, w.x, ft);
+                        t = fstep4<COLMODE>(t, w.y, ft);
+                        t = fstep4<COLMODE>(t, w.z, ft);
+                        t = fstep4<COLMODE>(t, w.w, ft);
+                        if (CP) hb |= w.x | w.y | w.z | w.w;
+                    }
+                    if (t != trap) {
+                        s = t;
+                        pos += kChunk;
+                        if (CP && (hb & 0x80808080u)) {
+                            // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
+                            // continuation bytes from the staged row again (volatile: do not keep 16 words live for this)
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                cpd += cont_bytes(*reinterpret_cast<const volatile uint32_t *>(row + j * 4));
+                        }
+                        return;
+                    }
+                    // something happened in these 64 bytes: go through them group by group below
+                    // (s and pos are untouched); only the group it happened in is redone exactly
+                }
+            }
+            generic(relk, row);
         };
         if (kmax) issue(Buf0{}, 0);
         for (uint32_t k = 0; k < kmax; k += 2) {

@@ -102,7 +102,7 @@ class _Automaton:
         return img
 
     # ---- the hot image (rows kept in shared memory), chosen from a sample of the data ----
-    HOT_TABLE_BYTES = 96 * 1024
+    HOT_TABLE_BYTES = 40 * 1024   # with 32 warps of staging buffers next to it, this is what fits on chip
 
     def _max_hot_rows(self):
         return max(2, min(4096, self.HOT_TABLE_BYTES // (2 * self.num_columns) - 1))
@@ -116,8 +116,10 @@ class _Automaton:
         rc = self._L.acb_hot_build(self._h, vp, rows, host.data_ptr(), nbytes)
         if rc != _capi.ACB_OK:
             raise RuntimeError(_capi.last_error())
-        n_rows = int(self._L.acb_hot_rows(host.data_ptr()))
-        return host.to(torch.device("cuda", idx)), n_rows
+        desc = _capi.HotDesc()
+        if self._L.acb_hot_describe(host.data_ptr(), C.byref(desc)) != _capi.ACB_OK:
+            raise RuntimeError(_capi.last_error())
+        return host.to(torch.device("cuda", idx)), desc
 
     def hot(self, device, data=None, offsets=None, overlapping=False):
         """The hot image on `device`.  Built from a profile of (data, offsets) the
@@ -238,7 +240,7 @@ class _Automaton:
             while True:
                 ws = self._workspace(dev, plan, n, cap)
                 st = self._ws_struct(ws)
-                rc = self._L.acb_scan_batch(self._h, img.data_ptr(), hot["tensor"].data_ptr(), hot["rows"],
+                rc = self._L.acb_scan_batch(self._h, img.data_ptr(), hot["tensor"].data_ptr(), C.byref(hot["rows"]),
                                             data.data_ptr(), offsets.data_ptr(), n, data.numel(),
                                             int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
@@ -250,6 +252,8 @@ class _Automaton:
                 total, complete, raw_total = tot[0], tot[1], tot[4]
                 self._note_trap_stats(hot, tot[2], tot[3])
                 self.last_stats = {"groups": tot[2], "traps": tot[3], "repairs": tot[5], "segments": plan.n_segments,
+                                   "hot_rows": hot["rows"].rows, "hot_rows128": hot["rows"].rows128,
+                                   "hot_visited": hot["rows"].visited,
                                    "segment_bytes": plan.segment_bytes, "lane_stride": plan.lane_stride}
                 if complete or (total == 0 and raw_total == 0):
                     return ws["out"][:total], ws["match_offsets"][: n + 1], total

@@ -112,6 +112,15 @@ int acb_hot_build(const acb_automaton *a, const uint32_t *host_visits, uint32_t 
                   uint64_t dst_bytes);
 uint32_t acb_hot_rows(const void *host_hot);
 
+/* What a hot image holds (read from its host copy; passed along with the device copy). */
+typedef struct acb_hot_desc {
+    uint32_t rows;     /* rows of the compact table (column-indexed) */
+    uint32_t rows128;  /* rows of the byte-indexed 128-wide table (0: patterns use bytes >= 0x7f) */
+    uint32_t visited;  /* rows the profile actually saw; the rest is filler */
+    uint32_t reserved;
+} acb_hot_desc;
+int acb_hot_describe(const void *host_hot, acb_hot_desc *desc);
+
 /*
  * How a scan is cut up.  The byte stream [offsets[0], offsets[n]) is divided into
  * fixed-size SEGMENTS on a grid anchored at the 64-byte aligned address at or
@@ -176,7 +185,7 @@ typedef struct acb_workspace {
  * overlapping on a non-Standard automaton returns ACB_EUNSUPPORTED before any
  * byte is read, like the reference.
  */
-int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, uint32_t hot_rows,
+int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, const acb_hot_desc *hot_desc,
                    const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
                    int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream);
 
@@ -197,7 +206,7 @@ typedef struct acb_tuning {
     int kernel;        /* 0 auto, 1 = plain (one thread per haystack, table in global/L2), 2 = staged segments */
     int hot_rows;      /* cap on rows kept in shared memory */
     int segment_bytes; /* segment size (rounded up to a multiple of 64 and to 8 x the warm-up) */
-    int reserved;
+    int table;         /* 0 auto, 1 = column-indexed compact table only, 2 = byte-indexed 128-wide table when available */
 } acb_tuning;
 int acb_set_tuning(const acb_tuning *t);
 

@@ -23,19 +23,24 @@ with open(os.path.join(HERE, "golden", "reference_vectors.json"), encoding="utf-
     VECTORS = json.load(f)["vectors"]
 
 
-def set_kernel(kernel=0, hot_rows=0, segment_bytes=0):
-    t = _capi.Tuning(kernel, hot_rows, segment_bytes, 0)
+def set_kernel(kernel=0, hot_rows=0, segment_bytes=0, table=0):
+    t = _capi.Tuning(kernel, hot_rows, segment_bytes, table)
     assert _capi.lib().acb_set_tuning(C.byref(t)) == 0
 
 
-@pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments"])
+@pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments", "staged-compact-table",
+                        "staged-byte-table-tiny"])
 def kernel(request):
     if request.param == "plain":
         set_kernel(1)
     elif request.param == "staged":
-        set_kernel(2)
+        set_kernel(2)                 # auto: byte-indexed table when the patterns are ASCII and the hot rows fit
     elif request.param == "staged-tiny-hot":
-        set_kernel(2, 5)  # 5 hot rows: nearly every group traps, exercising the exact/fast hand-over
+        set_kernel(2, 5, 0, 1)        # 5 hot rows, compact table: nearly every group leaves the hot set
+    elif request.param == "staged-compact-table":
+        set_kernel(2, 0, 0, 1)        # column-indexed table even where the byte-indexed one would do
+    elif request.param == "staged-byte-table-tiny":
+        set_kernel(2, 7, 256, 2)      # byte-indexed table forced, 7 rows, 256-byte segments
     else:
         set_kernel(2, 0, 128)  # 128-byte segments: speculative starts and the repair pass everywhere
     yield request.param

@@ -208,6 +208,35 @@ def test_profiled_hot_set_keeps_results_and_cuts_traps():
     assert len(set(h2f[:rows].tolist())) == rows and all(f2h[h2f[i]] == i for i in range(rows))
 
 
+def test_byte_indexed_table_agrees_with_compact_table():
+    import struct
+    from ahocorasick_rs_b200 import _capi
+    pats = [b"hello", b"help", b"world", b"wor", b"~x"]
+    for kind in range(3):
+        im = ii.Image(pats, kind)
+        L = im._L
+        n = L.acb_hot_bytes(im._h, 40)
+        buf = np.zeros(n, dtype=np.uint8)
+        assert L.acb_hot_build(im._h, None, 40, buf.ctypes.data, n) == 0
+        desc = _capi.HotDesc()
+        assert L.acb_hot_describe(buf.ctypes.data, __import__("ctypes").byref(desc)) == 0
+        assert desc.rows == min(40, im.n_states - 1) and desc.rows128 == desc.rows and desc.visited == 1
+        magic, rows, n_cols, n_states, o_t, o_h2f, o_f2h, total, rows128, visited, o_t128 = struct.unpack_from("<4I4Q2IQ", buf.tobytes()[:64])
+        t = buf[o_t:o_t + 2 * (rows + 1) * n_cols].view(np.uint16).reshape(rows + 1, n_cols) // (2 * n_cols)
+        t128 = buf[o_t128:o_t128 + 2 * (rows128 + 1) * 128].view(np.uint16).reshape(rows128 + 1, 128) // 256
+        for h in range(rows128 + 1):
+            for b in range(128):
+                assert t128[h, b] == t[h, im.col(b)]
+    # a pattern byte >= 0x7f rules the byte-indexed table out
+    im = ii.Image([b"caf\xc3\xa9"], 0)
+    n = im._L.acb_hot_bytes(im._h, 40)
+    buf = np.zeros(n, dtype=np.uint8)
+    assert im._L.acb_hot_build(im._h, None, 40, buf.ctypes.data, n) == 0
+    desc = _capi.HotDesc()
+    im._L.acb_hot_describe(buf.ctypes.data, __import__("ctypes").byref(desc))
+    assert desc.rows128 == 0
+
+
 def test_builder_errors():
     with pytest.raises(ValueError):
         ii.Image([b"a", b""])
