@@ -259,8 +259,6 @@ Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_
     off = align16(off + n * 4 + 4);
     h.off_pat_cplen = off;
     off = align16(off + n * 4 + 4);
-    h.off_match_first = off;
-    off = align16(off + uint64_t(n_states) * 8);
     h.total_bytes = off;
     try {
         A->image.assign(off, 0);
@@ -276,14 +274,6 @@ Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_
     if (n) {
         std::memcpy(img + h.off_pat_len, pat_len.data(), n * 4);
         std::memcpy(img + h.off_pat_cplen, pat_cplen.data(), n * 4);
-    }
-    {
-        uint32_t *mf = reinterpret_cast<uint32_t *>(img + h.off_match_first);
-        for (uint32_t s = 0; s < n_states; s++)
-            if (match_off[s + 1] != match_off[s]) {
-                mf[2 * s] = match_pid[match_off[s]];
-                mf[2 * s + 1] = pat_len[match_pid[match_off[s]]];
-            }
     }
     // dense rows, in id order: a row starts as a copy of its failure target's row
     // (already final, smaller id) and then takes the state's own trie edges

@@ -42,7 +42,6 @@ struct ImageHeader {
     uint64_t off_pat_len;    // u32[n_patterns] bytes
     uint64_t off_pat_cplen;  // u32[n_patterns] code points (non-continuation bytes)
     uint64_t total_bytes;
-    uint64_t off_match_first;  // {u32 pattern, u32 length}[n_states]: head of each state's match list (0,0 if none)
 };
 
 constexpr uint32_t kImageMagic = 0x30424341u;  // "ACB0"

@@ -222,7 +222,7 @@ match_offsets_kernel(const acb_match *out, const unsigned long long *unit_offset
 }
 
 __global__ void clear_totals_kernel(unsigned long long *totals, unsigned int *task_counter) {
-    if (threadIdx.x < 16) totals[threadIdx.x] = 0;  // [8..15]: timeline counters of debug builds
+    if (threadIdx.x < 8) totals[threadIdx.x] = 0;
     if (threadIdx.x == 0) *task_counter = 0;
 }
 
@@ -419,7 +419,6 @@ DevImage make_view(const ImageHeader &h, const void *dev_image) {
     im.match_pid = reinterpret_cast<const uint32_t *>(b + h.off_match_pid);
     im.pat_len = reinterpret_cast<const uint32_t *>(b + h.off_pat_len);
     im.pat_cplen = reinterpret_cast<const uint32_t *>(b + h.off_pat_cplen);
-    im.match_first = reinterpret_cast<const uint2 *>(b + h.off_match_first);
     im.n_cols = h.n_cols;
     im.col_lo = h.col_lo;
     im.n_states = h.n_states;
@@ -475,18 +474,16 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     const uint32_t stage_bytes = (uint32_t)warps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
-    uint32_t rows = (budget - stage_bytes - kStageOffset - 256) / (row_bytes + 4);  // includes the trap row; + 4 bytes of hot2full per row
-    if (COLMODE == kColAscii) rows -= 1;                                        // ... and the guard row behind it
+    uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
     uint32_t H = rows - 1;
     const uint32_t have = COLMODE == kColAscii ? hot.n_rows128 : hot.n_rows;
     if (H > have) H = have;
     if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
     if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
-    const uint32_t table_bytes = (((H + 1 + (COLMODE == kColAscii ? 1 : 0)) * row_bytes) + 127u) & ~127u;
-    const uint32_t hot_bytes = table_bytes + (((H + 1) * 4 + 127u) & ~127u);  // + the hot2full map
+    const uint32_t hot_bytes = (((H + 1) * row_bytes) + 127u) & ~127u;
     const uint32_t smem = hot_bytes + kStageOffset + stage_bytes;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-    kern<<<ctas, warps * 32, smem, st>>>(im, hot, B, P, out, seg_info, H, hot_bytes, table_bytes, task_counter, trap_stats);
+    kern<<<ctas, warps * 32, smem, st>>>(im, hot, B, P, out, seg_info, H, hot_bytes, task_counter, trap_stats);
     g_launches++;
     return ACB_OK;
 }
@@ -496,7 +493,7 @@ uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
     const uint32_t stage_bytes = 32u * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 128 + 2 * kAsciiCols * 2) return 0;
-    return (budget - stage_bytes - kStageOffset - 256) / (kAsciiCols * 2 + 4) - 2;  // minus the trap row and the guard row
+    return (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2) - 1;
 }
 
 template <int MODE, bool CP>
@@ -626,9 +623,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         uint32_t fit128 = ascii_rows_that_fit(d);
         if (fit128 > hot.n_rows128) fit128 = hot.n_rows128;
         if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < fit128) fit128 = (uint32_t)g_tuning.hot_rows;
-        // (measured: the byte-indexed table only pays on pure-ASCII input -- chunks with a high byte are scanned
-        // twice -- and the kernel is bound by shared-memory load issue either way, so it is opt-in)
-        const bool ascii = g_tuning.table == 2 && fit128 > 0;
+        const bool ascii = g_tuning.table != 1 && fit128 > 0 && (g_tuning.table == 2 || fit128 >= hot_desc->visited);
         // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
         // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
         P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);

@@ -35,7 +35,6 @@ struct DevImage {
     const uint32_t *match_pid;
     const uint32_t *pat_len;
     const uint32_t *pat_cplen;
-    const uint2 *match_first;  // {pattern, length} of the first entry of each state's match list
     uint32_t n_cols, col_lo, n_states, col_mode;
 };
 

@@ -252,10 +252,9 @@ __device__ __noinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im,
 template <int MODE, bool CP, int COLMODE>
 __global__ void __launch_bounds__(1024, 1)
 scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, SegInfo *seg_info, uint32_t H,
-                   uint32_t hot_bytes, uint32_t table_bytes, unsigned int *task_counter, unsigned long long *trap_stats) {
+                   uint32_t hot_bytes, unsigned int *task_counter, unsigned long long *trap_stats) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t *hot = smem;
-    uint32_t *h2f = reinterpret_cast<uint32_t *>(smem + table_bytes);  // hot index -> state id, (H + 1) entries
     uint8_t *cmap = smem + hot_bytes;                     // 256 B
     uint8_t *stage_all = smem + hot_bytes + kStageOffset;  // 128-aligned by construction
     const uint32_t row_entries = COLMODE == kColAscii ? kAsciiCols : im.n_cols;
@@ -274,11 +273,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(hot), src_table, bytes, bar);
         }
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
-        if (COLMODE == kColAscii) {
-            // guard row behind the trap row: the speculative (unclamped) pass may read up to 254 bytes past it
-            uint16_t *h16 = reinterpret_cast<uint16_t *>(hot);
-            for (uint32_t i = threadIdx.x; i < kAsciiCols; i += blockDim.x) h16[(H + 1) * kAsciiCols + i] = (uint16_t)trap;
-        }
         __syncthreads();  // the barrier is initialised before anyone polls it
         mbar_wait(bar, 0);
     } else {
@@ -292,10 +286,9 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             dst32[i] = min(v & 0xffffu, trap) | (min(v >> 16, trap) << 16);
         }
         if ((n & 1u) && threadIdx.x == 0) h16[n - 1] = (uint16_t)min((uint32_t)__ldg(src_table + n - 1), trap);
-        for (uint32_t i = threadIdx.x; i < row_entries * (COLMODE == kColAscii ? 2u : 1u); i += blockDim.x) h16[n + i] = (uint16_t)trap;
+        for (uint32_t i = threadIdx.x; i < row_entries; i += blockDim.x) h16[n + i] = (uint16_t)trap;
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
     }
-    for (uint32_t i = threadIdx.x; i <= H; i += blockDim.x) h2f[i] = __ldg(hot_img.hot2full + i);
     __syncthreads();
 
     HotMap hm;
@@ -307,15 +300,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     ft.lo = im.col_lo;
     ft.maxc = im.n_cols - 1;
     uint32_t n_groups = 0, n_traps = 0;
-#ifdef ACB_TIMELINE
-    // debug build: where does a warp's time go?  [0] total [1] task setup [2] waiting for staged bytes [3] scanning chunks
-    long long tl_t0 = clock64(), tl_setup = 0, tl_wait = 0, tl_scan = 0, tl_mark = 0;
-#define TL_MARK() (tl_mark = clock64())
-#define TL_ADD(acc) do { const long long n_ = clock64(); (acc) += n_ - tl_mark; tl_mark = n_; } while (0)
-#else
-#define TL_MARK() ((void)0)
-#define TL_ADD(acc) ((void)0)
-#endif
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint2 *meta = reinterpret_cast<uint2 *>(stage_all + (size_t)warp * kMetaBytes);
@@ -330,7 +314,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
 
     for (;;) {
         // ---- claim the next warp-task: 32 segments, lane_stride apart -----------------
-        TL_MARK();
         unsigned int task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
@@ -435,7 +418,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         };
         // hand the lane over to the exact scanner at position `pos`, come back at the next fast-resume point
         auto leave_fast = [&](uint32_t min_at) {
-            c.state = h2f[s / row_bytes];
+            c.state = __ldg(hot_img.hot2full + s / row_bytes);
             c.at = pos;
             if (CP) {
                 c.cp_pos = pos;
@@ -459,7 +442,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         auto piece_end_fast = [&]() -> bool {
             if (warm) {
                 // arrived at the segment start in state s: that is the guess; scan the head piece from it
-                L.spec_state = h2f[s / row_bytes];
+                L.spec_state = __ldg(hot_img.hot2full + s / row_bytes);
                 L.kind = kPieceHead;
                 stop = min(L.hi_rel, c.limit);
                 c.stop = stop;
@@ -472,7 +455,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // end of the segment: write the summary
                 uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
                 const uint32_t nem = c.nemit;
-                dst[0] = make_uint4(L.spec_state, h2f[s / row_bytes], 0u,
+                dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + s / row_bytes), 0u,
                                     L.kind == kPieceHead ? nem : L.head_count);
                 dst[1] = make_uint4(0u, CP ? cpd : 0u, 0u, 0u);
                 out.unit_counts[2 * L.seg] = 0;
@@ -484,19 +467,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             return false;
         };
 
-        // report a match found by the fast path itself (same record as scan_core.cuh: report)
-        auto emit_fast = [&](uint32_t pid, uint32_t len, uint32_t end, uint32_t cont_end) {
-            if (end <= c.emit_from) return;
-            const uint32_t hend = end + c.hay_delta;
-            const unsigned long long i = atomicAdd(out.raw_total, 1ULL);
-            if (i < out.cap) {
-                reinterpret_cast<uint4 *>(out.raw)[i] = make_uint4(c.hay, pid, hend - len, hend);
-                out.raw_seq[i] = c.nemit;
-                out.raw_unit[i] = c.unit;
-                if (CP) out.raw_aux[i] = cont_end;
-            }
-            c.nemit++;
-        };
         // everything that is not a clean whole chunk: 16-byte groups, then single bytes (one instance of this code)
         auto generic = [&](uint32_t relk, const uint8_t *row) {
 #pragma unroll 1
@@ -537,33 +507,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                         if (CP) cpd += (b & 0xC0u) == 0x80u;
                     } else {
                         trapped = true;
-                        if (MODE != kModeLeftmost) {
-                            // the common reason to leave the hot set is a match: resolve this one byte against
-                            // the full table right here instead of handing the lane to the exact scanner
-                            const uint32_t full = h2f[s / row_bytes];
-                            const uint32_t col = im.col_mode == kColRange ? min(b - im.col_lo, im.n_cols - 1) : (uint32_t)cmap[b];
-                            const uint32_t e = __ldg(im.trans + (size_t)full * im.n_cols + col);
-                            const uint32_t tfull = e & kStateMask;
-                            const uint32_t thot = (MODE == kModeStandard && (e & kMatchFlag)) ? 0u : (uint32_t)__ldg(hot_img.full2hot + tfull);
-                            if ((e & kMatchFlag) && thot < H) {
-                                const uint32_t end = pos + 1;
-                                const uint32_t cont_end = CP ? cpd + ((b & 0xC0u) == 0x80u) : 0u;
-                                if (MODE == kModeStandard) {
-                                    const uint2 mf = __ldg(im.match_first + tfull);
-                                    emit_fast(mf.x, mf.y, end, cont_end);
-                                } else {
-                                    const uint32_t m0 = __ldg(im.match_off + tfull), m1 = __ldg(im.match_off + tfull + 1);
-                                    for (uint32_t k = m0; k < m1; k++) {
-                                        const uint32_t pid = __ldg(im.match_pid + k);
-                                        emit_fast(pid, __ldg(im.pat_len + pid), end, cont_end);
-                                    }
-                                }
-                                s = thot * row_bytes;  // Standard: back at the root (hot row 0); overlapping: the match state itself
-                                pos = end;
-                                if (CP) cpd = cont_end;
-                                continue;
-                            }
-                        }
                         leave_fast(pos + 1);
                     }
                 }
@@ -575,10 +518,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         const uint8_t *row0 = stage + lane * kRow;
         auto body = [&](auto buf_tag, uint32_t k) {
             constexpr uint32_t BUF = decltype(buf_tag)::value;
-            TL_ADD(tl_scan);
             cp_async_wait_all();
             __syncwarp();
-            TL_ADD(tl_wait);
             if (k + 1 < kmax) issue(std::integral_constant<uint32_t, 1 - BUF>{}, k + 1);
             const uint8_t *row = row0 + BUF * kStageBytes;
             const uint32_t relk = k * kChunk;
@@ -587,22 +528,27 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // ---- the whole 64-byte chunk in the fast path: one trap check for all of it ----
                 uint32_t t = s, hb = 0;
                 if (COLMODE == kColAscii) {
-                    // raw-byte indexing, no clamp: speculative.  A byte >= 128 would index past its row
-                    // (still inside this CTA's shared memory, so harmless) and the result is thrown away:
-                    // the OR of all words tells afterwards whether that happened.
+                    // raw-byte indexing is only valid without high bytes: look first (separate loads, so
+                    // that the 16 words are not kept in registers across the scan)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
-                        t = fstep4<COLMODE, false>(t, w.x, ft);
-                        t = fstep4<COLMODE, false>(t, w.y, ft);
-                        t = fstep4<COLMODE, false>(t, w.z, ft);
-                        t = fstep4<COLMODE, false>(t, w.w, ft);
+                        const uint4 w = lds128_volatile(row + j * 16);
                         hb |= w.x | w.y | w.z | w.w;
                     }
-                    if (!(hb & 0x80808080u) && t != trap) {
-                        s = t;
-                        pos += kChunk;
-                        return;
+                    if (!(hb & 0x80808080u)) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                            t = fstep4<COLMODE, false>(t, w.x, ft);
+                            t = fstep4<COLMODE, false>(t, w.y, ft);
+                            t = fstep4<COLMODE, false>(t, w.z, ft);
+                            t = fstep4<COLMODE, false>(t, w.w, ft);
+                        }
+                        if (t != trap) {
+                            s = t;
+                            pos += kChunk;
+                            return;
+                        }
                     }
                     // high bytes or an event: group by group below
                 } else {
@@ -634,7 +580,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             generic(relk, row);
         };
         if (kmax) issue(Buf0{}, 0);
-        TL_ADD(tl_setup);
         for (uint32_t k = 0; k < kmax; k += 2) {
             body(Buf0{}, k);
             if (k + 1 < kmax) body(Buf1{}, k + 1);
@@ -643,17 +588,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         while (!done) {
             if (!(pos == stop && piece_end_fast())) leave_fast(stop);
         }
-        TL_ADD(tl_scan);
     }
-#ifdef ACB_TIMELINE
-    if (lane == 0) {
-        atomicAdd(trap_stats + 8, (unsigned long long)(clock64() - tl_t0));
-        atomicAdd(trap_stats + 9, (unsigned long long)tl_setup);
-        atomicAdd(trap_stats + 10, (unsigned long long)tl_wait);
-        atomicAdd(trap_stats + 11, (unsigned long long)tl_scan);
-        atomicAdd(trap_stats + 12, 1ULL);
-    }
-#endif
     // how well the hot set fits the data: the host re-profiles when traps are frequent
 #pragma unroll
     for (int d = 16; d; d >>= 1) {

@@ -186,7 +186,7 @@ class _Automaton:
                 "unit_offsets": torch.empty(n_units + 1, dtype=torch.int64, device=dev),
                 "seg_info": torch.empty((n_seg, 8), dtype=torch.int32, device=dev),
                 "scratch": torch.empty(n_scr, dtype=torch.int64, device=dev),
-                "total": torch.zeros(16, dtype=torch.int64, device=dev),
+                "total": torch.zeros(8, dtype=torch.int64, device=dev),
                 "out": torch.empty((cap, 4), dtype=torch.int32, device=dev),
                 "match_offsets": torch.empty(n_hay + 1, dtype=torch.int64, device=dev),
             }
@@ -252,7 +252,6 @@ class _Automaton:
                 total, complete, raw_total = tot[0], tot[1], tot[4]
                 self._note_trap_stats(hot, tot[2], tot[3])
                 self.last_stats = {"groups": tot[2], "traps": tot[3], "repairs": tot[5], "segments": plan.n_segments,
-                                   "timeline": tot[10:15],
                                    "hot_rows": hot["rows"].rows, "hot_rows128": hot["rows"].rows128,
                                    "hot_visited": hot["rows"].visited,
                                    "segment_bytes": plan.segment_bytes, "lane_stride": plan.lane_stride}

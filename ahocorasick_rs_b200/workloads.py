@@ -37,7 +37,7 @@ def config1():
     return ["hello", "world", "fish"], hay
 
 
-def config2(n_haystacks=100_000, hay_bytes=4096, first_index=0, name_every=90):
+def config2(n_haystacks=100_000, hay_bytes=4096, first_index=0):
     """C2: names patterns; haystack i = the benchmark's template line formatted with
     (PATTERNS_LONG[i % 4244] if i % 90 == 0 else "notaperson", i)
     (benchmarks/test_comparison.py:22-31), repeated to >= hay_bytes UTF-8 bytes, cut at a
@@ -47,7 +47,7 @@ def config2(n_haystacks=100_000, hay_bytes=4096, first_index=0, name_every=90):
     out = np.full((n_haystacks, hay_bytes), 0x20, dtype=np.uint8)
     for r in range(n_haystacks):
         i = first_index + r
-        name = pats[i % len(pats)] if (name_every and i % name_every == 0) else "notaperson"
+        name = pats[i % len(pats)] if i % 90 == 0 else "notaperson"
         line = tmpl.format(name, i).encode("utf-8")
         reps = -(-hay_bytes // len(line))
         buf = (line * reps)[: hay_bytes + 4]

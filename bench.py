@@ -155,7 +155,6 @@ def main():
     ap.add_argument("--segment-bytes", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--hot-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--table", type=int, default=0, help=argparse.SUPPRESS)
-    ap.add_argument("--name-every", type=int, default=90, help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -190,7 +189,7 @@ def main():
     batches = []
     pats = None
     for b in range(2):
-        pats, data, offs = W.config2(n_hay, HAY_BYTES, first_index=(rank * 2 + b) * n_hay, name_every=args.name_every)
+        pats, data, offs = W.config2(n_hay, HAY_BYTES, first_index=(rank * 2 + b) * n_hay)
         batches.append((data, offs))
     ac = AhoCorasick(pats, implementation=Implementation.DFA)
     d_batches = [(torch.from_numpy(d).to(dev), torch.from_numpy(o).to(dev)) for d, o in batches]

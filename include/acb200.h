@@ -156,7 +156,7 @@ typedef struct acb_workspace {
     uint64_t *dev_unit_offsets;  /* [plan.n_units + 1] */
     void *dev_seg_info;          /* [plan.n_segments * 32 bytes] per-segment summaries */
     uint64_t *dev_scratch;       /* [plan.scratch_words] */
-    uint64_t *dev_total;         /* [16]: [0] = matches found, [1] = 1 when dev_out holds all of them (0: buffers too
+    uint64_t *dev_total;         /* [8]: [0] = matches found, [1] = 1 when dev_out holds all of them (0: buffers too
                                     small, retry), [2] = 16-byte groups the fast path tried, [3] = groups handed to the
                                     exact scanner, [4] = raw matches emitted, [5] = segment boundaries repaired */
     acb_match *dev_out;          /* [out_capacity] final matches in the reference's order */
