@@ -475,12 +475,13 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
     uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
+    if (COLMODE == kColAscii) rows -= 1;                                        // ... and the guard row behind it
     uint32_t H = rows - 1;
     const uint32_t have = COLMODE == kColAscii ? hot.n_rows128 : hot.n_rows;
     if (H > have) H = have;
     if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
     if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
-    const uint32_t hot_bytes = (((H + 1) * row_bytes) + 127u) & ~127u;
+    const uint32_t hot_bytes = (((H + 1 + (COLMODE == kColAscii ? 1 : 0)) * row_bytes) + 127u) & ~127u;
     const uint32_t smem = hot_bytes + kStageOffset + stage_bytes;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     kern<<<ctas, warps * 32, smem, st>>>(im, hot, B, P, out, seg_info, H, hot_bytes, task_counter, trap_stats);
@@ -493,7 +494,7 @@ uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
     const uint32_t stage_bytes = 32u * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 128 + 2 * kAsciiCols * 2) return 0;
-    return (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2) - 1;
+    return (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2) - 2;  // minus the trap row and the guard row
 }
 
 template <int MODE, bool CP>
@@ -603,8 +604,6 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     const bool segments = kernel == 2;
     SegPlan P{};
     uint64_t n_units = (uint64_t)n_haystacks;
-    bool totals_flag_ascii = false;
-    (void)totals_flag_ascii;
 
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (g_timing) {
@@ -623,7 +622,10 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         uint32_t fit128 = ascii_rows_that_fit(d);
         if (fit128 > hot.n_rows128) fit128 = hot.n_rows128;
         if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < fit128) fit128 = (uint32_t)g_tuning.hot_rows;
-        const bool ascii = g_tuning.table != 1 && fit128 > 0 && (g_tuning.table == 2 || fit128 >= hot_desc->visited);
+        // Opt-in.  Measured on the config-2 text (about 1 chunk in 5 holds a multi-byte character and is
+        // scanned twice in this mode) it loses to the compact table: the kernel is bound by the issue rate
+        // of shared-memory loads, one per byte either way, not by the column arithmetic this saves.
+        const bool ascii = g_tuning.table == 2 && fit128 > 0;
         // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
         // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
         P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);
@@ -634,7 +636,6 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         P.avg_len = n_haystacks > 0 ? total_bytes / (uint64_t)n_haystacks : 0;
         n_units = 2 * plan->n_segments;
         rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st, ascii);
-        totals_flag_ascii = ascii;
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());
         if (ev1) {

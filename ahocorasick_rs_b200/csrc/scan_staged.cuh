@@ -273,6 +273,11 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(hot), src_table, bytes, bar);
         }
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
+        if (COLMODE == kColAscii) {
+            // guard row behind the trap row: the speculative (unclamped) pass may read up to 254 bytes past it
+            uint16_t *h16 = reinterpret_cast<uint16_t *>(hot);
+            for (uint32_t i = threadIdx.x; i < kAsciiCols; i += blockDim.x) h16[(H + 1) * kAsciiCols + i] = (uint16_t)trap;
+        }
         __syncthreads();  // the barrier is initialised before anyone polls it
         mbar_wait(bar, 0);
     } else {
@@ -286,7 +291,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             dst32[i] = min(v & 0xffffu, trap) | (min(v >> 16, trap) << 16);
         }
         if ((n & 1u) && threadIdx.x == 0) h16[n - 1] = (uint16_t)min((uint32_t)__ldg(src_table + n - 1), trap);
-        for (uint32_t i = threadIdx.x; i < row_entries; i += blockDim.x) h16[n + i] = (uint16_t)trap;
+        for (uint32_t i = threadIdx.x; i < row_entries * (COLMODE == kColAscii ? 2u : 1u); i += blockDim.x) h16[n + i] = (uint16_t)trap;
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
     }
     __syncthreads();
@@ -528,27 +533,22 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // ---- the whole 64-byte chunk in the fast path: one trap check for all of it ----
                 uint32_t t = s, hb = 0;
                 if (COLMODE == kColAscii) {
-                    // raw-byte indexing is only valid without high bytes: look first (separate loads, so
-                    // that the 16 words are not kept in registers across the scan)
+                    // raw-byte indexing, no clamp: speculative.  A byte >= 128 would index past its row
+                    // (into the next rows / the guard row, never outside the table) and the result is thrown
+                    // away: the OR of all words tells afterwards whether that happened.
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
-                        const uint4 w = lds128_volatile(row + j * 16);
+                        const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                        t = fstep4<COLMODE, false>(t, w.x, ft);
+                        t = fstep4<COLMODE, false>(t, w.y, ft);
+                        t = fstep4<COLMODE, false>(t, w.z, ft);
+                        t = fstep4<COLMODE, false>(t, w.w, ft);
                         hb |= w.x | w.y | w.z | w.w;
                     }
-                    if (!(hb & 0x80808080u)) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
-                            t = fstep4<COLMODE, false>(t, w.x, ft);
-                            t = fstep4<COLMODE, false>(t, w.y, ft);
-                            t = fstep4<COLMODE, false>(t, w.z, ft);
-                            t = fstep4<COLMODE, false>(t, w.w, ft);
-                        }
-                        if (t != trap) {
-                            s = t;
-                            pos += kChunk;
-                            return;
-                        }
+                    if (!(hb & 0x80808080u) && t != trap) {
+                        s = t;
+                        pos += kChunk;
+                        return;
                     }
                     // high bytes or an event: group by group below
                 } else {
