@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libacb200.so")
+# ACB200_LIB: another build of the same library (kernel experiments); the default is the in-tree build
+LIB_PATH = os.environ.get("ACB200_LIB") or os.path.join(HERE, "libacb200.so")
 
 ACB_OK = 0
 ACB_EINVAL, ACB_EBUILD, ACB_EUNSUPPORTED, ACB_ECUDA, ACB_ECAPACITY = -1, -2, -3, -4, -5

@@ -4,7 +4,10 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
+#include <cmath>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "repair.cuh"
 #include "scan_staged.cuh"
@@ -99,20 +102,19 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return before + x - v;
 }
 
-// in[i * stride] for i in [0, n)
-__global__ void __launch_bounds__(kScanThreads)
-scan_tile_sums(const uint32_t *in, uint32_t stride, uint64_t n, unsigned long long *tile_sums) {
-    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+// in[i * stride] for i in [0, n); one tile
+__device__ __forceinline__ void tile_sum_body(const uint32_t *in, uint32_t stride, uint64_t n, unsigned long long *tile_sums, uint64_t tile) {
+    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     unsigned long long v = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++)
         if (base + i < n) v += in[(base + i) * stride];
     unsigned long long total;
     block_exclusive_scan(v, &total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+    if (threadIdx.x == 0) tile_sums[tile] = total;
 }
 
-__global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(unsigned long long *tile_sums, uint64_t n_tiles) {
+__device__ __forceinline__ void tile_offsets_body(unsigned long long *tile_sums, uint64_t n_tiles) {
     unsigned long long carry = 0;
     for (uint64_t base = 0; base < n_tiles; base += kScanThreads) {
         const uint64_t i = base + threadIdx.x;
@@ -124,9 +126,9 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_offsets(unsigned long 
     }
 }
 
-__global__ void __launch_bounds__(kScanThreads)
-scan_apply(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long long *tile_offs, unsigned long long *out) {
-    const uint64_t base = (uint64_t)blockIdx.x * kScanTile + (uint64_t)threadIdx.x * kScanItems;
+__device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long long *tile_offs,
+                                                unsigned long long *out, uint64_t tile) {
+    const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     unsigned long long vals[kScanItems], v = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
@@ -134,7 +136,7 @@ scan_apply(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long 
         v += vals[i];
     }
     unsigned long long total;
-    unsigned long long run = tile_offs[blockIdx.x] + block_exclusive_scan(v, &total);
+    unsigned long long run = tile_offs[tile] + block_exclusive_scan(v, &total);
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
         if (base + i < n) out[base + i] = run;
@@ -142,6 +144,7 @@ scan_apply(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long 
         if (base + i + 1 == n) out[n] = run;
     }
 }
+
 
 // ---------------------------------------------------------------------------
 // final placement: raw match i of unit u with rank r goes to unit_offsets[u] + r
@@ -164,7 +167,7 @@ struct OrderArgs {
     unsigned long long out_cap;
 };
 
-__global__ void __launch_bounds__(256) order_matches_kernel(OrderArgs A) {
+__device__ __forceinline__ void order_body(const OrderArgs &A) {
     unsigned long long n = *A.raw_total;
     if (n > A.raw_cap) n = A.raw_cap;
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
@@ -199,9 +202,9 @@ __global__ void __launch_bounds__(256) order_matches_kernel(OrderArgs A) {
 }
 
 // per-haystack CSR offsets into the ordered output (binary search per haystack) + the totals
-__global__ void __launch_bounds__(256)
-match_offsets_kernel(const acb_match *out, const unsigned long long *unit_offsets, uint64_t n_units, unsigned long long *totals,
-                     unsigned long long raw_cap, unsigned long long out_cap, int64_t n_haystacks, unsigned long long *match_offsets) {
+__device__ __forceinline__ void
+match_offsets_body(const acb_match *out, const unsigned long long *unit_offsets, uint64_t n_units, unsigned long long *totals,
+                   unsigned long long raw_cap, unsigned long long out_cap, int64_t n_haystacks, unsigned long long *match_offsets) {
     const unsigned long long total = unit_offsets[n_units];
     const unsigned long long avail = total < out_cap ? total : out_cap;
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
@@ -219,6 +222,54 @@ match_offsets_kernel(const acb_match *out, const unsigned long long *unit_offset
             totals[1] = (totals[4] <= raw_cap && total <= out_cap) ? 1 : 0;  // complete?
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// everything after the scan in ONE cooperative kernel (grid-wide barriers
+// between the phases): repair -> prefix sums -> ordered output -> per-haystack
+// offsets.  Ten tiny launches cost more than the work they do.
+// ---------------------------------------------------------------------------
+struct EpilogueArgs {
+    DevImage im;
+    Batch B;
+    SegPlan P;
+    Sink out;
+    SegInfo *seg_info;
+    unsigned long long *totals;
+    const uint32_t *unit_counts;
+    uint64_t n_units;
+    unsigned long long *tile_sums, *unit_offsets;
+    const uint32_t *cont_tail;  // null: no code point prefix needed
+    uint64_t n_segments;
+    unsigned long long *cont_tiles, *cont_cum;
+    OrderArgs order;
+    unsigned long long *match_offsets;
+    int do_repair;
+};
+
+template <int MODE, bool CP>
+__global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    if (E.do_repair) {
+        repair_body<MODE, CP>(E.im, E.B, E.P, E.out, E.seg_info, E.totals + 5);
+        grid.sync();
+    }
+    const uint64_t tiles = (E.n_units + kScanTile - 1) / kScanTile;
+    const uint64_t ctiles = E.cont_tail ? (E.n_segments + kScanTile - 1) / kScanTile : 0;
+    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_sum_body(E.unit_counts, 1, E.n_units, E.tile_sums, t);
+    for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_sum_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, t);
+    grid.sync();
+    if (blockIdx.x == 0) tile_offsets_body(E.tile_sums, tiles);
+    if (ctiles && blockIdx.x == (gridDim.x > 1 ? 1 : 0)) tile_offsets_body(E.cont_tiles, ctiles);
+    grid.sync();
+    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_apply_body(E.unit_counts, 1, E.n_units, E.tile_sums, E.unit_offsets, t);
+    for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_apply_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, E.cont_cum, t);
+    grid.sync();
+    order_body(E.order);
+    grid.sync();
+    match_offsets_body(E.order.out, E.unit_offsets, E.n_units, E.totals, E.order.raw_cap, E.order.out_cap, E.B.n_haystacks,
+                       E.match_offsets);
 }
 
 __global__ void clear_totals_kernel(unsigned long long *totals, unsigned int *task_counter) {
@@ -469,7 +520,21 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     const int ctas = d.sms;
     int warps = (int)((tasks + ctas - 1) / ctas);
     if (warps < 4) warps = 4;
-    if (warps > 32) warps = 32;
+#ifndef ACB_BALANCE
+#define ACB_BALANCE 1
+#endif
+    if (warps > kMaxWarps && !ACB_BALANCE) warps = kMaxWarps;
+    if (warps > kMaxWarps) {
+        // every warp runs ceil(tasks / warps) tasks in the worst case: of the CTA sizes near the maximum take
+        // the one that wastes the least of its last round (12 500 tasks: 32 warps -> 2.64 tasks per warp,
+        // 88 % busy; 29 warps -> 2.91, 97 %)
+        double best = 0;
+        for (int w = kMaxWarps; w >= kMaxWarps - 6; w--) {
+            const double per = (double)tasks / ((double)ctas * w);
+            const double eff = per / std::ceil(per) * (1.0 - 0.01 * (kMaxWarps - w));
+            if (eff > best + 1e-9) best = eff, warps = w;
+        }
+    }
     const uint32_t row_bytes = COLMODE == kColAscii ? kAsciiCols * 2 : im.n_cols * 2;
     const uint32_t stage_bytes = (uint32_t)warps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
@@ -491,7 +556,7 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
 
 // how many 128-wide rows fit next to the staging buffers of a full CTA
 uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
-    const uint32_t stage_bytes = 32u * (2 * kStageBytes + kMetaBytes);
+    const uint32_t stage_bytes = (uint32_t)kMaxWarps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 128 + 2 * kAsciiCols * 2) return 0;
     return (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2) - 2;  // minus the trap row and the guard row
@@ -508,13 +573,17 @@ int launch_staged_cols(const ImageHeader &h, const DevImage &im, const DevHot &h
 }
 
 template <int MODE, bool CP>
-int launch_repair(const DevImage &im, const Batch &B, const SegPlan &P, const Sink &out, SegInfo *seg_info,
-                  unsigned long long *stats, const DeviceInfo &d, cudaStream_t st) {
-    int64_t blocks = (B.n_haystacks + 127) / 128;
-    const int64_t cap = (int64_t)d.sms * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    repair_kernel<MODE, CP><<<(unsigned)blocks, 128, 0, st>>>(im, B, P, out, seg_info, stats);
+int launch_epilogue(EpilogueArgs &E, const DeviceInfo &d, cudaStream_t st) {
+    auto kern = epilogue_kernel<MODE, CP>;
+    static thread_local int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    int &bps = blocks_per_sm[MODE][CP ? 1 : 0];
+    if (bps == 0) {
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kScanThreads, 0));
+        if (bps < 1) return fail(ACB_ECUDA, "epilogue kernel does not fit on an SM");
+        if (bps > 4) bps = 4;
+    }
+    void *args[] = {&E};
+    CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * bps), dim3(kScanThreads), args, 0, st));
     g_launches++;
     return ACB_OK;
 }
@@ -642,11 +711,6 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
             CUDA_OK(cudaEventRecord(ev1, st));
             g_timing_events.emplace_back(ev0, ev1);
         }
-        if (mode != kModeOverlap) {
-            rc = ACB_DISPATCH(launch_repair, im, B, P, out, seg_info, totals + 5, d, st);
-            if (rc) return rc;
-            CUDA_OK(cudaGetLastError());
-        }
     } else {
         rc = ACB_DISPATCH(launch_plain, im, B, out, d, st);
         if (rc) return rc;
@@ -656,27 +720,11 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
             g_timing_events.emplace_back(ev0, ev1);
         }
     }
-#undef ACB_DISPATCH
-
-    // counts -> offsets -> ordered output -> per-haystack offsets
-    const uint64_t tiles = (n_units + kScanTile - 1) / kScanTile;
-    unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
-    scan_tile_sums<<<(unsigned)tiles, kScanThreads, 0, st>>>(ws->dev_unit_counts, 1, n_units, tile_sums);
-    scan_tile_offsets<<<1, kScanThreads, 0, st>>>(tile_sums, tiles);
-    scan_apply<<<(unsigned)tiles, kScanThreads, 0, st>>>(ws->dev_unit_counts, 1, n_units, tile_sums, unit_offsets);
-    g_launches += 3;
+    // repair -> counts -> offsets -> ordered output -> per-haystack offsets: one cooperative kernel
     const uint64_t max_tiles = (plan->n_units + kScanTile - 1) / kScanTile;
+    unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
     unsigned long long *cont_tiles = tile_sums + max_tiles + 1;
     unsigned long long *cont_cum = cont_tiles + max_tiles + 1;
-    if (segments && cp) {
-        // exclusive prefix sum of SegInfo.cont_tail (8 u32 per segment, field 5)
-        const uint64_t ns = plan->n_segments, t2 = (ns + kScanTile - 1) / kScanTile;
-        const uint32_t *ct = reinterpret_cast<const uint32_t *>(seg_info) + 5;
-        scan_tile_sums<<<(unsigned)t2, kScanThreads, 0, st>>>(ct, 8, ns, cont_tiles);
-        scan_tile_offsets<<<1, kScanThreads, 0, st>>>(cont_tiles, t2);
-        scan_apply<<<(unsigned)t2, kScanThreads, 0, st>>>(ct, 8, ns, cont_tiles, cont_cum);
-        g_launches += 3;
-    }
     OrderArgs A;
     A.raw = ws->dev_raw;
     A.raw_seq = ws->dev_raw_seq;
@@ -694,10 +742,27 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     A.codepoints = cp ? 1 : 0;
     A.out = ws->dev_out;
     A.out_cap = ws->out_capacity;
-    order_matches_kernel<<<d.sms * 4, 256, 0, st>>>(A);
-    match_offsets_kernel<<<d.sms * 2, 256, 0, st>>>(ws->dev_out, unit_offsets, n_units, totals, ws->raw_capacity, ws->out_capacity,
-                                                    n_haystacks, match_offsets);
-    g_launches += 2;
+    EpilogueArgs E;
+    E.im = im;
+    E.B = B;
+    E.P = P;
+    E.out = out;
+    E.seg_info = seg_info;
+    E.totals = totals;
+    E.unit_counts = ws->dev_unit_counts;
+    E.n_units = n_units;
+    E.tile_sums = tile_sums;
+    E.unit_offsets = unit_offsets;
+    E.cont_tail = (segments && cp) ? reinterpret_cast<const uint32_t *>(seg_info) + 5 : nullptr;
+    E.n_segments = plan->n_segments;
+    E.cont_tiles = cont_tiles;
+    E.cont_cum = cont_cum;
+    E.order = A;
+    E.match_offsets = match_offsets;
+    E.do_repair = (segments && mode != kModeOverlap) ? 1 : 0;
+    rc = ACB_DISPATCH(launch_epilogue, E, d, st);
+#undef ACB_DISPATCH
+    if (rc) return rc;
     CUDA_OK(cudaGetLastError());
     return ACB_OK;
 }

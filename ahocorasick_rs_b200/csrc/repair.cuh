@@ -42,8 +42,8 @@ __device__ __forceinline__ void machine_step(PieceCtx &m, const DevImage &im, Em
 }
 
 template <int MODE, bool CP>
-__global__ void __launch_bounds__(128)
-repair_kernel(DevImage im, Batch B, SegPlan P, Sink out, SegInfo *seg_info, unsigned long long *stats) {
+__device__ __forceinline__ void repair_body(const DevImage &im, const Batch &B, const SegPlan &P, const Sink &out,
+                                            SegInfo *seg_info, unsigned long long *stats) {
     const int64_t stream_hi = __ldg(B.offsets + B.n_haystacks);
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
         const int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);

@@ -44,6 +44,10 @@
 
 namespace acb {
 
+#ifndef ACB_MAX_WARPS
+#define ACB_MAX_WARPS 32
+#endif
+constexpr int kMaxWarps = ACB_MAX_WARPS;  // per CTA (one CTA per SM): 32 -> 64 registers per thread, 28 -> 72, 24 -> 80
 constexpr int kChunk = 64;                // bytes per lane per stage
 constexpr int kRow = kChunk + 16;         // a lane's row in the staging buffer: 80-byte pitch = conflict-free LDS.128 without a swizzle
 constexpr int kStageBytes = 32 * kRow;    // per warp per buffer
@@ -250,7 +254,7 @@ __device__ __noinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im,
 }
 
 template <int MODE, bool CP, int COLMODE>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
 scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, SegInfo *seg_info, uint32_t H,
                    uint32_t hot_bytes, unsigned int *task_counter, unsigned long long *trap_stats) {
     extern __shared__ __align__(128) uint8_t smem[];

@@ -215,6 +215,7 @@ def main():
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    host_t0 = time.perf_counter()
     for i in range(args.steps):
         out, moffs, tot = step(i)
         if world > 1:
@@ -222,6 +223,7 @@ def main():
             n_local = totals[i & 1]
             gather_match_lists(out[:n_local], hay_base=(rank * 2 + (i & 1)) * n_hay)
     ev1.record()
+    host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / max(args.steps, 1)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -294,6 +296,7 @@ def main():
                 "steps": e2e_steps, "api": "AhoCorasick.scan_device on pinned host tensors copied H2D inside the timed region, matches copied back"},
         "gpu_launches": launches,
         "scan_stats": scan_stats,
+        "host_enqueue_ms_per_step": host_enqueue_ms,
         "clocks": clocks,
     }
     if not args.no_cpu_baseline:
