@@ -540,6 +540,8 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
     uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
+    // table entries are 16-bit shared-memory ADDRESSES: the table (it starts dynamic shared memory) must end below 64 KB
+    if (rows > (60u * 1024u) / row_bytes) rows = (60u * 1024u) / row_bytes;
     if (COLMODE == kColAscii) rows -= 1;                                        // ... and the guard row behind it
     uint32_t H = rows - 1;
     const uint32_t have = COLMODE == kColAscii ? hot.n_rows128 : hot.n_rows;
@@ -559,7 +561,9 @@ uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
     const uint32_t stage_bytes = (uint32_t)kMaxWarps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 128 + 2 * kAsciiCols * 2) return 0;
-    return (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2) - 2;  // minus the trap row and the guard row
+    uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2);
+    if (rows > (60u * 1024u) / (kAsciiCols * 2)) rows = (60u * 1024u) / (kAsciiCols * 2);  // 16-bit row addresses
+    return rows - 2;  // minus the trap row and the guard row
 }
 
 template <int MODE, bool CP>

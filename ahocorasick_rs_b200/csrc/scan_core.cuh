@@ -191,7 +191,7 @@ __device__ __forceinline__ bool leftmost_flush(PieceCtx &c, uint32_t &s, uint32_
 //   at >= min_at, the state is hot and nothing is pending,
 // i.e. at a point where the staged fast path may take over again.
 template <int MODE, bool CP>
-__device__ __noinline__ void exact_scan(PieceCtx &c, const DevImage &im_in, const Sink &out, bool stop_hot,
+__device__ __forceinline__ void exact_scan(PieceCtx &c, const DevImage &im_in, const Sink &out, bool stop_hot,
                                         uint32_t min_at, HotMap hm) {
     const DevImage im = im_in;  // private copy: the loop keeps the table pointers in registers
     uint32_t s = c.state, at = c.at;

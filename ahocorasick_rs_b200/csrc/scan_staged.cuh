@@ -8,18 +8,30 @@
 //        visit counts).  An entry is the BYTE OFFSET of the next state's row
 //        inside this table when that state is hot and is neither a match state
 //        nor the dead state, else the offset of row H, the TRAP row, which maps
-//        everything to itself.  One add therefore forms the next shared-memory
-//        address, a lane that left the hot set stays trapped, and ONE compare
-//        per 16 bytes detects it; the 16 bytes are then redone by exact_scan
-//        from the saved state.  Brought in with one TMA bulk copy
-//        (cp.async.bulk + mbarrier) when the whole hot image fits.
+//        everything to itself.  Brought in with one TMA bulk copy
+//        (cp.async.bulk + mbarrier) when the whole hot image fits; the CTA then
+//        adds the table's own shared-memory address to every entry, so an entry
+//        IS the 32-bit shared address of the next row: one three-input add
+//        (row + column + column) forms the next load address, with nothing else
+//        on the dependent chain.  A lane that left the hot set stays trapped and
+//        ONE compare per 64 bytes detects it; only the group something happened
+//        in is redone, through the exact scanner.  (Addresses must fit 16 bits:
+//        the table lives in the first 64 KB of shared memory.)
 //   [ column map : 256 B ]  (kColClass only)
 //   [ mbarrier ]
 //   [ copy metadata : per warp 32 x (first 16-byte unit, number of chunks) ]
-//   [ staging : per warp, 2 buffers x 32 lanes x 80 B ]  lane l's 64-byte
-//        chunk at a pitch of 80 bytes: consecutive lanes start 5 sixteen-byte
-//        units apart, so the per-lane LDS.128 reads of a quarter warp hit 8
-//        different bank groups (conflict free) with plain immediate offsets.
+//   [ staging : per warp, 2 buffers x 32 lanes x 64 B ]  lane l's 64-byte
+//        chunk is row l, with its four 16-byte units XOR-swizzled by
+//        (l >> 1) & 3: the per-lane LDS.128 reads of a quarter warp hit 8
+//        different bank groups (conflict free), and a warp-wide cp.async
+//        instruction (8 rows) fills four whole 128-byte lines of shared
+//        memory.  (An 80-byte pitch without a swizzle reads just as well, but
+//        every copy instruction then straddles 12-14 lines: ncu showed 14
+//        shared-memory wavefronts per LDGSTS instead of 4.)
+//
+// All shared-memory traffic of the scan loop goes through explicit 32-bit
+// shared addresses (inline PTX): the swizzle is an XOR on the address, and the
+// table loads must not pick up a base-address add on the dependent chain.
 //
 // Work decomposition (scan_core.cuh: SegPlan).  The stream is cut into
 // fixed-size segments; a lane scans one segment, walking through whatever
@@ -49,29 +61,65 @@ namespace acb {
 #endif
 constexpr int kMaxWarps = ACB_MAX_WARPS;  // per CTA (one CTA per SM): 32 -> 64 registers per thread, 28 -> 72, 24 -> 80
 constexpr int kChunk = 64;                // bytes per lane per stage
-constexpr int kRow = kChunk + 16;         // a lane's row in the staging buffer: 80-byte pitch = conflict-free LDS.128 without a swizzle
+constexpr int kRow = kChunk;              // a lane's row in the staging buffer; its 16-byte units are swizzled by (lane >> 1) & 3
 constexpr int kStageBytes = 32 * kRow;    // per warp per buffer
 constexpr int kStageOffset = 256 + 128;   // column map + mbarrier slot, after the hot table
 constexpr int kMetaBytes = 32 * 8;        // per warp: (first 16-byte unit, chunk count) of each lane, read by the copy issue
 
 struct FastTab {
-    const uint8_t *hot;   // shared: the table, addressed in bytes
-    const uint8_t *cmap;  // shared: byte -> column (kColClass)
+    uint32_t cmap;  // shared address of the byte -> column map (kColClass)
     uint32_t lo, maxc;
 };
 
+// ---- shared memory by 32-bit shared address ----
+// Table loads: the table never changes after the prologue, so the load is a pure function of its
+// address (not volatile: the compiler may schedule it freely).
+__device__ __forceinline__ uint32_t lds_tab(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u16 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_tab_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+// Staged bytes and copy metadata: volatile, the same address holds different data from one chunk to the next.
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};\n" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+// a lane's staged row: `row` is the address of its 16-byte unit 0; unit j and byte p of the swizzled row
+__device__ __forceinline__ uint32_t row_unit(uint32_t row, uint32_t j) { return row ^ (j << 4); }
+__device__ __forceinline__ uint32_t row_byte(uint32_t row, uint32_t p) { return (row ^ (p & 0x30u)) + (p & 15u); }
+
 constexpr int kColAscii = 2;  // hot table indexed by the raw byte (128 entries per row); bytes >= 128 clamp to 127
 
+// one transition: s is the shared address of the current row, the result that of the next
 template <int COLMODE, bool CLAMP = true>
 __device__ __forceinline__ uint32_t fstep(uint32_t s, uint32_t b, const FastTab &f) {
     uint32_t col;
     if (COLMODE == kColRange)
         col = min(b - f.lo, f.maxc);
     else if (COLMODE == kColClass)
-        col = (uint32_t)f.cmap[b];
+        col = lds_tab_u8(f.cmap + b);
     else
         col = CLAMP ? min(b, 127u) : b;
-    return *reinterpret_cast<const uint16_t *>(f.hot + s + (col << 1));
+    return lds_tab(s + col + col);
 }
 
 template <int COLMODE, bool CLAMP = true>
@@ -81,14 +129,6 @@ __device__ __forceinline__ uint32_t fstep4(uint32_t s, uint32_t w, const FastTab
     s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4442), f);
     s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4443), f);
     return s;
-}
-
-__device__ __forceinline__ uint4 lds128_volatile(const uint8_t *p) {
-    uint4 v;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
-    return v;
 }
 
 // continuation bytes (10xxxxxx) in a word
@@ -153,7 +193,7 @@ struct LaneSeg {
 // The current piece is finished (c.at >= c.stop, nothing pending): move on.  Either starts the next
 // piece (c.at = its first byte, c.state = its start state) or sets L.done and writes the segment summary.
 template <int MODE, bool CP>
-__device__ __noinline__ void advance_piece(PieceCtx &c, LaneSeg &L, const Batch &B, const Sink &out, SegInfo *seg_info) {
+__device__ __forceinline__ void advance_piece(PieceCtx &c, LaneSeg &L, const Batch &B, const Sink &out, SegInfo *seg_info) {
     bool finish_segment = false;
     if (L.kind == kPieceWarm) {
         const uint32_t he_rel = c.limit;
@@ -239,7 +279,7 @@ __device__ __noinline__ void advance_piece(PieceCtx &c, LaneSeg &L, const Batch 
 // Runs the exact scanner until the lane is at a point where the fast path can take over
 // (hot state, nothing pending, inside a piece) or the segment is finished.
 template <int MODE, bool CP>
-__device__ __noinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im, const Batch &B, const Sink &out,
+__device__ __forceinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im, const Batch &B, const Sink &out,
                                     SegInfo *seg_info, HotMap hm, uint32_t min_at) {
     for (;;) {
         exact_scan<MODE, CP>(c, im, out, true, min_at, hm);
@@ -258,68 +298,85 @@ __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, SegInfo *seg_info, uint32_t H,
                    uint32_t hot_bytes, unsigned int *task_counter, unsigned long long *trap_stats) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t *hot = smem;
-    uint8_t *cmap = smem + hot_bytes;                     // 256 B
-    uint8_t *stage_all = smem + hot_bytes + kStageOffset;  // 128-aligned by construction
+    const uint32_t hot_s = (uint32_t)__cvta_generic_to_shared(smem);  // the table; also the address of hot row 0 (the root)
+    const uint32_t cmap_s = hot_s + hot_bytes;                        // 256 B
+    const uint32_t bar_s = cmap_s + 256;                              // mbarrier, then the stream bounds (2 x int64)
+    const uint32_t stage_all_s = cmap_s + kStageOffset;               // 128-aligned by construction
     const uint32_t row_entries = COLMODE == kColAscii ? kAsciiCols : im.n_cols;
     const uint32_t row_bytes = row_entries * 2;
-    const uint32_t trap = H * row_bytes;
+    const uint32_t trap_off = H * row_bytes;
+    const uint32_t trap = hot_s + trap_off;  // entries are shared ADDRESSES of rows (see the header comment)
     const uint16_t *src_table = COLMODE == kColAscii ? hot_img.table128 : hot_img.table;
+    uint8_t *cmap = smem + hot_bytes;
+    int64_t *bounds = reinterpret_cast<int64_t *>(smem + hot_bytes + 256 + 16);
 
     // ---- prologue: the hot table (L2 resident) ------------------------------------------
+    const uint32_t n_entries = (H + 1) * row_entries;
+    const uint32_t guard_entries = COLMODE == kColAscii ? kAsciiCols : 0;  // the speculative (unclamped) pass may read up to 254 bytes past the trap row
+    uint32_t *tab32 = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t bias2 = hot_s | (hot_s << 16);
     if (H == (COLMODE == kColAscii ? hot_img.n_rows128 : hot_img.n_rows)) {
         // the whole image fits: one TMA bulk copy, completion on an mbarrier
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem + hot_bytes + 256);
-        const uint32_t bytes = ((H + 1) * row_bytes + 15u) & ~15u;
+        const uint32_t bytes = (n_entries * 2 + 15u) & ~15u;
         if (threadIdx.x == 0) {
-            mbar_init(bar, 1);
-            mbar_expect_tx(bar, bytes);
-            tma_bulk_g2s((uint32_t)__cvta_generic_to_shared(hot), src_table, bytes, bar);
+            mbar_init(bar_s, 1);
+            mbar_expect_tx(bar_s, bytes);
+            tma_bulk_g2s(hot_s, src_table, bytes, bar_s);
+            bounds[0] = __ldg(B.offsets);
+            bounds[1] = __ldg(B.offsets + B.n_haystacks);
         }
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
-        if (COLMODE == kColAscii) {
-            // guard row behind the trap row: the speculative (unclamped) pass may read up to 254 bytes past it
-            uint16_t *h16 = reinterpret_cast<uint16_t *>(hot);
-            for (uint32_t i = threadIdx.x; i < kAsciiCols; i += blockDim.x) h16[(H + 1) * kAsciiCols + i] = (uint16_t)trap;
-        }
         __syncthreads();  // the barrier is initialised before anyone polls it
-        mbar_wait(bar, 0);
+        mbar_wait(bar_s, 0);
+        // offsets -> addresses (two entries per word; no carry: every address is below 64 K)
+        for (uint32_t i = threadIdx.x; i < (n_entries + 1) / 2; i += blockDim.x) tab32[i] += bias2;
     } else {
         // a prefix of the image (rows are hottest-first): entries beyond it become the trap
-        uint16_t *h16 = reinterpret_cast<uint16_t *>(hot);
         const uint32_t n = H * row_entries;
         const uint32_t *src32 = reinterpret_cast<const uint32_t *>(src_table);  // 16-byte aligned in the image
-        uint32_t *dst32 = reinterpret_cast<uint32_t *>(hot);
-        for (uint32_t i = threadIdx.x; i < n / 2; i += blockDim.x) {
+        for (uint32_t i = threadIdx.x; i < (n + 1) / 2; i += blockDim.x) {
             const uint32_t v = __ldg(src32 + i);
-            dst32[i] = min(v & 0xffffu, trap) | (min(v >> 16, trap) << 16);
+            tab32[i] = (min(v & 0xffffu, trap_off) | (min(v >> 16, trap_off) << 16)) + bias2;
         }
-        if ((n & 1u) && threadIdx.x == 0) h16[n - 1] = (uint16_t)min((uint32_t)__ldg(src_table + n - 1), trap);
-        for (uint32_t i = threadIdx.x; i < row_entries * (COLMODE == kColAscii ? 2u : 1u); i += blockDim.x) h16[n + i] = (uint16_t)trap;
+        __syncthreads();  // (an odd n: the word above also wrote the first trap-row entry; the fill below overwrites it)
+        uint16_t *h16 = reinterpret_cast<uint16_t *>(smem);
+        for (uint32_t i = threadIdx.x; i < row_entries; i += blockDim.x) h16[n + i] = (uint16_t)trap;
         for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) cmap[i] = __ldg(im.colmap + i);
+        if (threadIdx.x == 0) {
+            bounds[0] = __ldg(B.offsets);
+            bounds[1] = __ldg(B.offsets + B.n_haystacks);
+        }
+    }
+    {
+        uint16_t *h16 = reinterpret_cast<uint16_t *>(smem);
+        for (uint32_t i = threadIdx.x; i < guard_entries; i += blockDim.x) h16[n_entries + i] = (uint16_t)trap;
     }
     __syncthreads();
+    // 16-byte groups scanned, for the host's traps-per-group statistic (it re-profiles when traps are frequent)
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(trap_stats, (unsigned long long)((bounds[1] - bounds[0]) >> 4));
 
     HotMap hm;
     hm.full2hot = hot_img.full2hot;
     hm.hot_limit = H;
     FastTab ft;
-    ft.hot = hot;
-    ft.cmap = cmap;
+    ft.cmap = cmap_s;
     ft.lo = im.col_lo;
     ft.maxc = im.n_cols - 1;
-    uint32_t n_groups = 0, n_traps = 0;
+    // hot row index <-> row address
+    auto row_of = [&](uint32_t addr) { return (addr - hot_s) / row_bytes; };
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint2 *meta = reinterpret_cast<uint2 *>(stage_all + (size_t)warp * kMetaBytes);
-    uint8_t *stage = stage_all + (size_t)(blockDim.x >> 5) * kMetaBytes + (size_t)warp * 2 * kStageBytes;
-    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t meta_s = stage_all_s + warp * kMetaBytes;
+    const uint32_t stage_s = stage_all_s + (blockDim.x >> 5) * kMetaBytes + warp * 2 * kStageBytes;
     const uintptr_t gbase = reinterpret_cast<uintptr_t>(B.bytes + P.origin);  // 64-byte aligned by construction of the plan
-    // copy instruction i of a stage moves 16-byte unit (lane & 3) of lane (i * 8 + lane / 4)
-    const uint32_t cp_dst = stage_s + (lane >> 2) * kRow + (lane & 3) * 16;
-    const uint64_t q = P.lane_stride;
-    const uint64_t n_tasks = ((uint64_t)P.n_segments + 32 * q - 1) / (32 * q) * q;
-    const int64_t stream_lo = __ldg(B.offsets), stream_hi = __ldg(B.offsets + B.n_haystacks);
+    // copy instruction i of a stage moves 16-byte unit (lane & 3) of lane (i * 8 + lane / 4); the unit's
+    // place in its row is swizzled by (row >> 1) & 3, which does not depend on i
+    const uint32_t cp_dst = stage_s + (lane >> 2) * kRow + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
+    const uint32_t cp_meta = meta_s + (lane >> 2) * 8;
+    // this lane's own row: the address of its unit 0
+    const uint32_t row_s = stage_s + lane * kRow + (((lane >> 1) & 3) << 4);
+    const uint32_t q = P.lane_stride;
+    const uint32_t n_tasks = (uint32_t)(((uint64_t)P.n_segments + 32ull * q - 1) / (32ull * q) * q);
 
     for (;;) {
         // ---- claim the next warp-task: 32 segments, lane_stride apart -----------------
@@ -328,15 +385,24 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= n_tasks) break;
 
-        PieceCtx c;
-        LaneSeg L;
+        // The exact scanner's state and the segment bookkeeping live in LOCAL memory on purpose (their
+        // addresses are laundered through an empty asm so the compiler cannot promote the ~28 words to
+        // registers): only the careful path touches them, and the chunk loop needs the registers.
+        PieceCtx c_mem;
+        LaneSeg L_mem;
+        PieceCtx *c_ptr = &c_mem;
+        LaneSeg *L_ptr = &L_mem;
+        asm volatile("" : "+l"(c_ptr), "+l"(L_ptr));
+        PieceCtx &c = *c_ptr;
+        LaneSeg &L = *L_ptr;
         L.seg = (int64_t)(((uint64_t)(task / q) * 32 + lane) * q + task % q);
         L.done = 1;
         L.spec_state = kNoState;
         L.head_count = 0;
         uint32_t off16 = 0, nchunks = 0;
-        uint32_t pos = 0, s = 0, stop = 0, cpd = 0;
+        uint32_t pos = 0, s = hot_s, stop = 0, cpd = 0;
         bool warm = false;  // the current piece is the silent warm-up before the segment
+        const int64_t stream_lo = bounds[0], stream_hi = bounds[1];
         const int64_t glo = P.origin + L.seg * (int64_t)P.seg_bytes;
         const int64_t lo = max(glo, stream_lo), hi = min(glo + (int64_t)P.seg_bytes, stream_hi);
         if (L.seg < P.n_segments && lo >= hi) {
@@ -383,43 +449,26 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             c.cp_pos = c.at;
             c.cp_cont = 0;
             warm = cont;
-            if (c.at < c.stop) {
-                // a piece always starts in the root state, which is hot row 0: straight into the fast path
-                pos = c.at;
-                stop = c.stop;
-                s = 0;
-            } else {
-                settle<MODE, CP>(c, L, im, B, out, seg_info, hm, c.at);  // (cannot happen: segments are never empty here)
-                pos = c.at;
-                stop = c.stop;
-                warm = !L.done && L.kind == kPieceWarm;
-                if (!L.done) {
-                    s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
-                    if (CP) {
-                        cp_catch_up(c, pos);
-                        cpd = c.cp_cont;
-                    }
-                }
-            }
+            // the first piece is never empty (lo < hi, and a warm-up starts before lo) and starts in the
+            // root state, which is hot row 0: straight into the fast path
+            pos = c.at;
+            stop = c.stop;
         }
         bool done = L.done != 0;
         if (done) nchunks = 0;
-        uint32_t kmax = nchunks;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) kmax = max(kmax, __shfl_xor_sync(0xffffffffu, kmax, d));
+        const uint32_t kmax = __reduce_max_sync(0xffffffffu, nchunks);
         // where each lane's bytes are: read back by whichever lane copies them (no shuffles in the loop:
         // the compiler cannot prove the warp converged there and would emit a slow collective path)
         __syncwarp();  // the previous task no longer reads meta / the staging buffers
-        meta[lane] = make_uint2(off16, nchunks);
+        sts64(meta_s + lane * 8, make_uint2(off16, nchunks));
         __syncwarp();
-        if (!done) n_groups += (L.hi_rel - c.at) >> 4;
 
         // stage chunk k into buffer BUF (compile-time: every shared-memory address below is base + immediate)
         auto issue = [&](auto buf_tag, uint32_t k) {
             constexpr uint32_t BUF = decltype(buf_tag)::value;
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const uint2 m = meta[i * 8 + (lane >> 2)];
+                const uint2 m = lds64(cp_meta + i * 64);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + ((size_t)(m.x + k * 4 + (lane & 3)) << 4);
                 cp_async16(cp_dst + BUF * kStageBytes + i * 8 * kRow, src, k < m.y ? 16u : 0u);
             }
@@ -427,7 +476,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         };
         // hand the lane over to the exact scanner at position `pos`, come back at the next fast-resume point
         auto leave_fast = [&](uint32_t min_at) {
-            c.state = __ldg(hot_img.hot2full + s / row_bytes);
+            c.state = __ldg(hot_img.hot2full + row_of(s));
             c.at = pos;
             if (CP) {
                 c.cp_pos = pos;
@@ -439,7 +488,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             stop = c.stop;
             warm = !done && L.kind == kPieceWarm;
             if (!done) {
-                s = (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
+                s = hot_s + (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
                 if (CP) {
                     cp_catch_up(c, pos);
                     cpd = c.cp_cont;
@@ -451,7 +500,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         auto piece_end_fast = [&]() -> bool {
             if (warm) {
                 // arrived at the segment start in state s: that is the guess; scan the head piece from it
-                L.spec_state = __ldg(hot_img.hot2full + s / row_bytes);
+                L.spec_state = __ldg(hot_img.hot2full + row_of(s));
                 L.kind = kPieceHead;
                 stop = min(L.hi_rel, c.limit);
                 c.stop = stop;
@@ -464,7 +513,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // end of the segment: write the summary
                 uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
                 const uint32_t nem = c.nemit;
-                dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + s / row_bytes), 0u,
+                dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + row_of(s)), 0u,
                                     L.kind == kPieceHead ? nem : L.head_count);
                 dst[1] = make_uint4(0u, CP ? cpd : 0u, 0u, 0u);
                 out.unit_counts[2 * L.seg] = 0;
@@ -477,14 +526,14 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         };
 
         // everything that is not a clean whole chunk: 16-byte groups, then single bytes (one instance of this code)
-        auto generic = [&](uint32_t relk, const uint8_t *row) {
+        auto generic = [&](uint32_t relk, uint32_t row) {
 #pragma unroll 1
             for (int j = 0; j < 4; j++) {
                 const uint32_t g = relk + j * 16;
                 if (done || pos < g || pos >= g + 16) continue;  // this lane is not inside this group
                 if (pos == g && g + 16 <= stop) {
                     // a whole 16-byte group in the fast path
-                    const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
+                    const uint4 w = lds128(row_unit(row, (uint32_t)j));
                     uint32_t t = fstep4<COLMODE>(s, w.x, ft);
                     t = fstep4<COLMODE>(t, w.y, ft);
                     t = fstep4<COLMODE>(t, w.z, ft);
@@ -502,84 +551,73 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // byte by byte through the hot table (bytes from the staged row): piece boundaries,
                 // unaligned positions, and the group something happens in -- the exact scanner only
                 // gets the byte that left the hot set
-                bool trapped = false;
                 while (!done && pos >= g && pos < g + 16) {
+                    uint32_t min_at = stop;
                     if (pos >= stop) {
-                        if (!(pos == stop && piece_end_fast())) leave_fast(stop);
-                        continue;
-                    }
-                    const uint32_t b = row[pos - relk];
-                    const uint32_t t = fstep<COLMODE>(s, b, ft);
-                    if (t != trap) {
-                        s = t;
-                        pos++;
-                        if (CP) cpd += (b & 0xC0u) == 0x80u;
+                        if (pos == stop && piece_end_fast()) continue;
                     } else {
-                        trapped = true;
-                        leave_fast(pos + 1);
+                        const uint32_t b = lds8(row_byte(row, pos - relk));
+                        const uint32_t t = fstep<COLMODE>(s, b, ft);
+                        if (t != trap) {
+                            s = t;
+                            pos++;
+                            if (CP) cpd += (b & 0xC0u) == 0x80u;
+                            continue;
+                        }
+                        atomicAdd(trap_stats + 1, 1ULL);  // how well the hot set fits the data: the host re-profiles when traps are frequent
+                        min_at = pos + 1;
                     }
+                    leave_fast(min_at);  // (the one call into the exact scanner inside the chunk loop)
                 }
-                n_traps += trapped;
             }
         };
         using Buf0 = std::integral_constant<uint32_t, 0>;
         using Buf1 = std::integral_constant<uint32_t, 1>;
-        const uint8_t *row0 = stage + lane * kRow;
+        // One chunk: the whole 64 bytes through the table with one trap check when the lane is in the clean
+        // middle of a piece, else (a piece boundary, an unaligned start, a trap) the careful path.  The careful
+        // path is a structured branch of this body, so the warp reconverges before the next chunk.
         auto body = [&](auto buf_tag, uint32_t k) {
             constexpr uint32_t BUF = decltype(buf_tag)::value;
             cp_async_wait_all();
             __syncwarp();
             if (k + 1 < kmax) issue(std::integral_constant<uint32_t, 1 - BUF>{}, k + 1);
-            const uint8_t *row = row0 + BUF * kStageBytes;
+            const uint32_t row = row_s + BUF * kStageBytes;
             const uint32_t relk = k * kChunk;
             if (!done && warm && pos == stop && pos == relk) piece_end_fast();  // the warm-up ended right at this chunk
             if (!done && pos == relk && relk + kChunk <= stop) {
-                // ---- the whole 64-byte chunk in the fast path: one trap check for all of it ----
                 uint32_t t = s, hb = 0;
-                if (COLMODE == kColAscii) {
-                    // raw-byte indexing, no clamp: speculative.  A byte >= 128 would index past its row
-                    // (into the next rows / the guard row, never outside the table) and the result is thrown
-                    // away: the OR of all words tells afterwards whether that happened.
+                uint4 w = lds128(row);
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
-                        t = fstep4<COLMODE, false>(t, w.x, ft);
-                        t = fstep4<COLMODE, false>(t, w.y, ft);
-                        t = fstep4<COLMODE, false>(t, w.z, ft);
-                        t = fstep4<COLMODE, false>(t, w.w, ft);
-                        hb |= w.x | w.y | w.z | w.w;
-                    }
-                    if (!(hb & 0x80808080u) && t != trap) {
-                        s = t;
-                        pos += kChunk;
-                        return;
-                    }
-                    // high bytes or an event: group by group below
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint4 w = *reinterpret_cast<const uint4 *>(row + j * 16);
-                        t = fstep4<COLMODE>(t, w.x, ft);
-                        t = fstep4<COLMODE>(t, w.y, ft);
-                        t = fstep4<COLMODE>(t, w.z, ft);
-                        t = fstep4<COLMODE>(t, w.w, ft);
-                        if (CP) hb |= w.x | w.y | w.z | w.w;
-                    }
-                    if (t != trap) {
-                        s = t;
-                        pos += kChunk;
-                        if (CP && (hb & 0x80808080u)) {
-                            // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
-                            // continuation bytes from the staged row again (volatile: do not keep 16 words live for this)
-#pragma unroll
-                            for (int j = 0; j < 16; j++)
-                                cpd += cont_bytes(*reinterpret_cast<const volatile uint32_t *>(row + j * 4));
-                        }
-                        return;
-                    }
-                    // something happened in these 64 bytes: go through them group by group below
-                    // (s and pos are untouched); only the group it happened in is redone exactly
+                for (int j = 0; j < 4; j++) {
+                    uint4 wn = w;
+                    if (j < 3) wn = lds128(row_unit(row, (uint32_t)j + 1));  // in flight while unit j is scanned
+                    // (kColAscii: raw-byte indexing, no clamp, speculative.  A byte >= 128 would index past its
+                    // row -- into the next rows / the guard row, never outside the table -- and the result is
+                    // thrown away: the OR of all words tells afterwards whether that happened.)
+                    t = fstep4<COLMODE, false>(t, w.x, ft);
+                    t = fstep4<COLMODE, false>(t, w.y, ft);
+                    t = fstep4<COLMODE, false>(t, w.z, ft);
+                    t = fstep4<COLMODE, false>(t, w.w, ft);
+                    if (CP || COLMODE == kColAscii) hb |= w.x | w.y | w.z | w.w;
+                    w = wn;
                 }
+                const bool high = (hb & 0x80808080u) != 0;
+                if (t != trap && !(COLMODE == kColAscii && high)) {
+                    s = t;
+                    pos += kChunk;
+                    if (CP && high) {
+                        // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
+                        // continuation bytes from the staged row again (do not keep 16 words live for this)
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const uint4 v = lds128(row_unit(row, (uint32_t)j));
+                            cpd += cont_bytes(v.x) + cont_bytes(v.y) + cont_bytes(v.z) + cont_bytes(v.w);
+                        }
+                    }
+                    return;
+                }
+                // something happened in these 64 bytes (or, kColAscii, they hold high bytes); s and pos are
+                // untouched and the careful path goes through them group by group
             }
             generic(relk, row);
         };
@@ -592,16 +630,6 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         while (!done) {
             if (!(pos == stop && piece_end_fast())) leave_fast(stop);
         }
-    }
-    // how well the hot set fits the data: the host re-profiles when traps are frequent
-#pragma unroll
-    for (int d = 16; d; d >>= 1) {
-        n_groups += __shfl_xor_sync(0xffffffffu, n_groups, d);
-        n_traps += __shfl_xor_sync(0xffffffffu, n_traps, d);
-    }
-    if (lane == 0) {
-        atomicAdd(trap_stats, (unsigned long long)n_groups);
-        atomicAdd(trap_stats + 1, (unsigned long long)n_traps);
     }
 }
 
