@@ -90,12 +90,28 @@ class ClockSampler:
         return out
 
 
+def usable_cores() -> int:
+    """Host threads this process may really run: the affinity mask, cut down to the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def cpu_port_throughput(pats_bytes, data, offs, budget_s=12.0, threads=None):
     """Times the oracle port (dense DFA, one contiguous shard of haystacks per host
     thread) on a bounded sample of the same workload.  Returns (GB/s, matches/s, cores, sample)."""
     from oracle import Oracle
 
-    threads = threads or os.cpu_count() or 1
+    threads = threads or usable_cores()
     orc = Oracle(pats_bytes, "Standard")
     n = len(offs) - 1
     orc.time_batch(data, offs, codepoints=True, nthreads=threads, reps=1)  # warm + calibrate
@@ -123,7 +139,7 @@ def run_reference(args, rank, world):
     pb = [p.encode() for p in pats]
     from oracle import Oracle
 
-    threads = os.cpu_count() or 1
+    threads = usable_cores()
     orc = Oracle(pb, "Standard")
     orc.time_batch(data, offs, codepoints=True, nthreads=threads, reps=max(args.warmup, 1))
     t0 = time.perf_counter()
@@ -279,6 +295,14 @@ def main():
     alg_bytes = bytes_per_step + 8 * (n_hay + 1) + 16 * matches_per_step
     k_ms = kms.value / max(kn.value, 1)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    # DRAM bytes per launch of that kernel from the committed ncu capture (profiles/summarize.py), at the default
+    # workload size only: the capture is of this workload
+    traffic, traffic_src = None, None
+    tj = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_scan_kernel.json")
+    if os.path.exists(tj) and n_hay == 100_000:
+        with open(tj) as f:
+            t = json.load(f)
+        traffic, traffic_src = t["dram_traffic_bytes_per_launch"], "profiles/r01_scan_kernel.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)"
     line = {
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -289,7 +313,7 @@ def main():
         "matches_per_s": matches_per_step * args.steps * world / (ms_max * 1e-3),
         "matches_per_step_per_gpu": matches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "scan_staged_kernel",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "scan_staged_kernel",
                      "kernel_ms": k_ms, "algorithmic_bytes_per_launch": alg_bytes},
         "e2e": {"value": bytes_per_step * e2e_steps * world / e2e_s / 1e9, "unit": "GB/s",
                 "h2d_bytes_per_step": bytes_per_step + 8 * (n_hay + 1), "d2h_bytes_per_step": d2h // e2e_steps,
