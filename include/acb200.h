@@ -157,8 +157,8 @@ typedef struct acb_workspace {
     void *dev_seg_info;          /* [plan.n_segments * 32 bytes] per-segment summaries */
     uint64_t *dev_scratch;       /* [plan.scratch_words] */
     uint64_t *dev_total;         /* [8]: [0] = matches found, [1] = 1 when dev_out holds all of them (0: buffers too
-                                    small, retry), [2] = 16-byte groups the fast path tried, [3] = groups handed to the
-                                    exact scanner, [4] = raw matches emitted, [5] = segment boundaries repaired */
+                                    small, retry), [2] = 16-byte groups in the stream, [3] = times a lane left the hot table
+                                    for the exact scanner, [4] = raw matches emitted, [5] = segment boundaries repaired */
     acb_match *dev_out;          /* [out_capacity] final matches in the reference's order */
     uint64_t out_capacity;
     uint64_t *dev_match_offsets; /* [n_haystacks + 1] haystack h's matches are dev_out[off[h] .. off[h+1]) */
