@@ -63,31 +63,44 @@ def gather_match_lists(local, hay_base: int, group=None, dst: Optional[int] = No
     return torch.cat(parts, dim=0)
 
 
-def gather_match_lists_async(matches, status, hay_base: int, cap: int, group=None):
+class MatchListGather:
     """The same exchange without touching the host: nothing here waits for the
-    GPU, so a pipeline of scans keeps running.  matches: the (capacity, 4) int32
-    output buffer of scan_device(sync=False); status: its 8-entry device status
-    tensor (status[0] = number of valid rows).  Every rank contributes a fixed
-    (cap + 1, 4) block -- row 0 = (count, hay_base, complete flag, 0), then the
-    first `cap` rows -- in ONE all_gather.  Returns the (world, cap + 1, 4)
-    device tensor; decode_gathered() turns it into the ordered global list
-    (that is where the host finally looks at the counts)."""
-    import torch
-    import torch.distributed as dist
+    GPU, so a pipeline of scans keeps running.  Every rank contributes a fixed
+    (cap + 1, 4) int32 block -- row 0 = (count, hay_base, complete flag, 0),
+    then its first `cap` matches -- in ONE all_gather per call; the buffers are
+    allocated once.  decode_gathered() turns the result into the ordered global
+    list (that is where the host finally looks at the counts)."""
 
-    world = dist.get_world_size(group)
-    dev = matches.device
-    block = torch.empty((cap + 1, 4), dtype=torch.int32, device=dev)
-    k = min(cap, matches.shape[0])
-    block[1: k + 1] = matches[:k]
-    head = torch.zeros(4, dtype=torch.int64, device=dev)
-    head[0] = status[0]
-    head[1] = hay_base
-    head[2] = status[1]
-    block[0] = head.to(torch.int32)
-    everything = torch.empty(world * (cap + 1) * 4, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(everything, block.view(-1), group=group)
-    return everything.view(world, cap + 1, 4)
+    def __init__(self, cap: int, device, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.cap = cap
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.block = torch.zeros((cap + 1, 4), dtype=torch.int32, device=device)
+        self.everything = torch.empty(self.world * (cap + 1) * 4, dtype=torch.int32, device=device)
+
+    def __call__(self, matches, status, hay_base: int):
+        """matches: the (capacity, 4) int32 output buffer of scan_device(sync=False); status: its
+        8-entry int64 device status tensor ([0] = valid rows, [1] = complete flag).
+        Returns the (world, cap + 1, 4) device tensor (reused by the next call)."""
+        import torch.distributed as dist
+
+        k = min(self.cap, matches.shape[0])
+        self.block[1: k + 1].copy_(matches[:k])
+        lo = status.view(self.block.dtype)  # little-endian low words of the 64-bit counters
+        head = self.block[0]
+        head[0:1].copy_(lo[0:1])
+        head[2:3].copy_(lo[2:3])
+        head[1:2].fill_(hay_base)
+        dist.all_gather_into_tensor(self.everything, self.block.view(-1), group=self.group)
+        return self.everything.view(self.world, self.cap + 1, 4)
+
+
+def gather_match_lists_async(matches, status, hay_base: int, cap: int, group=None):
+    """One-shot form of MatchListGather (allocates its buffers)."""
+    return MatchListGather(cap, matches.device, group)(matches, status, hay_base)
 
 
 def decode_gathered(gathered):

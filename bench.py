@@ -186,7 +186,7 @@ def main():
     import torch.distributed as dist
 
     from ahocorasick_rs_b200 import AhoCorasick, Implementation, _capi, workloads as W
-    from ahocorasick_rs_b200.sharding import decode_gathered, gather_match_lists_async
+    from ahocorasick_rs_b200.sharding import MatchListGather, decode_gathered
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -223,6 +223,11 @@ def main():
     totals = [int(ac.scan_device(*d_batches[b], capacity=cap)[2]) for b in range(2)]
     scan_stats = dict(ac._ac.last_stats)
     gather_cap = max(4096, -(-2 * max(totals) // 4096) * 4096)  # rows per rank in the match-list gather (multi-GPU)
+    gather = MatchListGather(gather_cap, dev) if world > 1 else None
+    if world > 1:
+        for i in range(max(args.warmup, 3)):  # warm the exchange too (communicator set-up, buffers)
+            o_, _, t_ = step(i)
+            gather(o_, t_, (rank * 2 + (i & 1)) * n_hay)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -238,7 +243,7 @@ def main():
         if world > 1:
             # the only exchange of the path: gather the per-shard match lists (sparse, a few KB)
             # (fixed-size blocks, no host round trip: the scans of the next steps are enqueued meanwhile)
-            gathered = gather_match_lists_async(out, tot, hay_base=(rank * 2 + (i & 1)) * n_hay, cap=gather_cap)
+            gathered = gather(out, tot, (rank * 2 + (i & 1)) * n_hay)
     ev1.record()
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / max(args.steps, 1)
     if world > 1 and args.steps > 0:
