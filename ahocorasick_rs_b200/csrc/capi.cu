@@ -114,20 +114,19 @@ __device__ __forceinline__ void tile_sum_body(const uint32_t *in, uint32_t strid
     if (threadIdx.x == 0) tile_sums[tile] = total;
 }
 
-__device__ __forceinline__ void tile_offsets_body(unsigned long long *tile_sums, uint64_t n_tiles) {
-    unsigned long long carry = 0;
-    for (uint64_t base = 0; base < n_tiles; base += kScanThreads) {
-        const uint64_t i = base + threadIdx.x;
-        const unsigned long long v = i < n_tiles ? tile_sums[i] : 0;
-        unsigned long long total;
-        const unsigned long long ex = block_exclusive_scan(v, &total);
-        if (i < n_tiles) tile_sums[i] = carry + ex;
-        carry += total;
-    }
+// sum of tile_sums[0 .. tile): every block works out the start of its own tile (a few hundred values at most for a
+// batch, a few thousand for a multi-gigabyte buffer) instead of waiting for one block to scan them all
+__device__ __forceinline__ unsigned long long tile_prefix(const unsigned long long *tile_sums, uint64_t tile) {
+    unsigned long long v = 0;
+    for (uint64_t i = threadIdx.x; i < tile; i += kScanThreads) v += tile_sums[i];
+    unsigned long long total;
+    block_exclusive_scan(v, &total);
+    return total;
 }
 
-__device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long long *tile_offs,
+__device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long long *tile_sums,
                                                 unsigned long long *out, uint64_t tile) {
+    const unsigned long long tile_start = tile_prefix(tile_sums, tile);
     const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     unsigned long long vals[kScanItems], v = 0;
 #pragma unroll
@@ -136,7 +135,7 @@ __device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t str
         v += vals[i];
     }
     unsigned long long total;
-    unsigned long long run = tile_offs[tile] + block_exclusive_scan(v, &total);
+    unsigned long long run = tile_start + block_exclusive_scan(v, &total);
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
         if (base + i < n) out[base + i] = run;
@@ -244,6 +243,7 @@ struct EpilogueArgs {
     unsigned long long *cont_tiles, *cont_cum;
     OrderArgs order;
     unsigned long long *match_offsets;
+    unsigned int *need_repair;  // zeroed with the totals; set when a speculated segment start was wrong
     int do_repair;
 };
 
@@ -251,21 +251,38 @@ template <int MODE, bool CP>
 __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    if (E.do_repair) {
-        repair_body<MODE, CP>(E.im, E.B, E.P, E.out, E.seg_info, E.totals + 5);
-        grid.sync();
-    }
     const uint64_t tiles = (E.n_units + kScanTile - 1) / kScanTile;
     const uint64_t ctiles = E.cont_tail ? (E.n_segments + kScanTile - 1) / kScanTile : 0;
-    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_sum_body(E.unit_counts, 1, E.n_units, E.tile_sums, t);
-    for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_sum_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, t);
+    auto sums = [&]() {
+        for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_sum_body(E.unit_counts, 1, E.n_units, E.tile_sums, t);
+        for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_sum_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, t);
+    };
+    // phase 1: tile sums of the counts as the scan kernel left them, and -- non-overlapping searches -- the check of
+    // every speculated segment start against the state its predecessor ended in (repair.cuh has the same rule)
+    if (E.do_repair) {
+        unsigned int dirty = 0;
+        for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; k < E.n_segments; k += (uint64_t)gridDim.x * blockDim.x) {
+            const uint32_t spec = E.seg_info[k].spec_state;
+            if (spec == kNoState) continue;  // the segment starts with a haystack (or outside all of them)
+            const uint4 prev = *reinterpret_cast<const uint4 *>(E.seg_info + k - 1);  // spec, end_state, end_over, head_count
+            dirty |= (prev.z != 0 || prev.y != spec) ? 1u : 0u;
+        }
+        if (__any_sync(0xffffffffu, dirty) && (threadIdx.x & 31) == 0) atomicOr(E.need_repair, 1u);
+    }
+    sums();
     grid.sync();
-    if (blockIdx.x == 0) tile_offsets_body(E.tile_sums, tiles);
-    if (ctiles && blockIdx.x == (gridDim.x > 1 ? 1 : 0)) tile_offsets_body(E.cont_tiles, ctiles);
-    grid.sync();
+    if (E.do_repair && *reinterpret_cast<volatile unsigned int *>(E.need_repair)) {
+        // rare: some guess was wrong.  Redo those places exactly, then count again.
+        repair_body<MODE, CP>(E.im, E.B, E.P, E.out, E.seg_info, E.totals + 5);
+        grid.sync();
+        sums();
+        grid.sync();
+    }
+    // phase 2: exclusive prefix sums (every block derives its tile's start from the tile sums)
     for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_apply_body(E.unit_counts, 1, E.n_units, E.tile_sums, E.unit_offsets, t);
     for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_apply_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, E.cont_cum, t);
     grid.sync();
+    // phase 3: ordered output; phase 4: per-haystack offsets into it
     order_body(E.order);
     grid.sync();
     match_offsets_body(E.order.out, E.unit_offsets, E.n_units, E.totals, E.order.raw_cap, E.order.out_cap, E.B.n_haystacks,
@@ -274,7 +291,7 @@ __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) 
 
 __global__ void clear_totals_kernel(unsigned long long *totals, unsigned int *task_counter) {
     if (threadIdx.x < 8) totals[threadIdx.x] = 0;
-    if (threadIdx.x == 0) *task_counter = 0;
+    if (threadIdx.x < 2) task_counter[threadIdx.x] = 0;  // [0] the scan kernel's task queue, [1] the epilogue's "repair needed" flag
 }
 
 // when the input is empty: nothing ran, publish zeros
@@ -763,6 +780,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     E.cont_cum = cont_cum;
     E.order = A;
     E.match_offsets = match_offsets;
+    E.need_repair = task_counter + 1;
     E.do_repair = (segments && mode != kModeOverlap) ? 1 : 0;
     rc = ACB_DISPATCH(launch_epilogue, E, d, st);
 #undef ACB_DISPATCH
