@@ -528,32 +528,33 @@ int launch_plain(const DevImage &im, const Batch &B, const Sink &out, const Devi
     return ACB_OK;
 }
 
-template <int MODE, bool CP, int COLMODE>
+template <int MODE, bool CP, int COLMODE, int V>
 int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const SegPlan &P, const Sink &out, SegInfo *seg_info,
                   const DeviceInfo &d, unsigned int *task_counter, unsigned long long *trap_stats, cudaStream_t st) {
-    auto kern = scan_staged_kernel<MODE, CP, COLMODE>;
+    auto kern = scan_staged_kernel<MODE, CP, COLMODE, V>;
+    constexpr int kWarpsMax = V == 1 ? kMaxWarps : kMaxWarps2;
     const uint64_t q = P.lane_stride;
-    const uint64_t tasks = ((uint64_t)P.n_segments + 32 * q - 1) / (32 * q) * q;
+    const uint64_t tasks = ((uint64_t)P.n_segments + 32 * V * q - 1) / (32 * V * q) * q;
     const int ctas = d.sms;
     int warps = (int)((tasks + ctas - 1) / ctas);
     if (warps < 4) warps = 4;
 #ifndef ACB_BALANCE
 #define ACB_BALANCE 1
 #endif
-    if (warps > kMaxWarps && !ACB_BALANCE) warps = kMaxWarps;
-    if (warps > kMaxWarps) {
+    if (warps > kWarpsMax && !ACB_BALANCE) warps = kWarpsMax;
+    if (warps > kWarpsMax) {
         // every warp runs ceil(tasks / warps) tasks in the worst case: of the CTA sizes near the maximum take
         // the one that wastes the least of its last round (12 500 tasks: 32 warps -> 2.64 tasks per warp,
         // 88 % busy; 29 warps -> 2.91, 97 %)
         double best = 0;
-        for (int w = kMaxWarps; w >= kMaxWarps - 6; w--) {
+        for (int w = kWarpsMax; w >= kWarpsMax - 4; w--) {
             const double per = (double)tasks / ((double)ctas * w);
-            const double eff = per / std::ceil(per) * (1.0 - 0.01 * (kMaxWarps - w));
+            const double eff = per / std::ceil(per) * (1.0 - 0.01 * (kWarpsMax - w));
             if (eff > best + 1e-9) best = eff, warps = w;
         }
     }
     const uint32_t row_bytes = COLMODE == kColAscii ? kAsciiCols * 2 : im.n_cols * 2;
-    const uint32_t stage_bytes = (uint32_t)warps * (2 * kStageBytes + kMetaBytes);
+    const uint32_t stage_bytes = (uint32_t)warps * V * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
     uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
@@ -586,11 +587,14 @@ uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
 template <int MODE, bool CP>
 int launch_staged_cols(const ImageHeader &h, const DevImage &im, const DevHot &hot, const Batch &B, const SegPlan &P, const Sink &out,
                        SegInfo *seg_info, const DeviceInfo &d, unsigned int *task_counter, unsigned long long *trap_stats,
-                       cudaStream_t st, bool ascii) {
-    if (ascii) return launch_staged<MODE, CP, kColAscii>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
-    if (h.col_mode == kColRange)
-        return launch_staged<MODE, CP, kColRange>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
-    return launch_staged<MODE, CP, kColClass>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st);
+                       cudaStream_t st, bool ascii, int per_lane) {
+#define ACB_GO(COLS)                                                                                                        \
+    (per_lane == 2 ? launch_staged<MODE, CP, COLS, 2>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st)      \
+                   : launch_staged<MODE, CP, COLS, 1>(im, hot, B, P, out, seg_info, d, task_counter, trap_stats, st))
+    if (ascii) return ACB_GO(kColAscii);
+    if (h.col_mode == kColRange) return ACB_GO(kColRange);
+    return ACB_GO(kColClass);
+#undef ACB_GO
 }
 
 template <int MODE, bool CP>
@@ -691,7 +695,8 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     int kernel = g_tuning.kernel;
     if (kernel == 0) kernel = 2;
     if (!dev_hot || !hot_desc) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
-    const bool segments = kernel == 2;
+    const bool segments = kernel == 2 || kernel == 3;
+    const int per_lane = kernel == 3 ? 2 : 1;  // segments per lane of the staged kernel (3: two interleaved chains)
     SegPlan P{};
     uint64_t n_units = (uint64_t)n_haystacks;
 
@@ -725,7 +730,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         P.lane_stride = plan->lane_stride;
         P.avg_len = n_haystacks > 0 ? total_bytes / (uint64_t)n_haystacks : 0;
         n_units = 2 * plan->n_segments;
-        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st, ascii);
+        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st, ascii, per_lane);
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());
         if (ev1) {

@@ -60,11 +60,15 @@ namespace acb {
 #define ACB_MAX_WARPS 32
 #endif
 constexpr int kMaxWarps = ACB_MAX_WARPS;  // per CTA (one CTA per SM): 32 -> 64 registers per thread, 28 -> 72, 24 -> 80
+#ifndef ACB_MAX_WARPS2
+#define ACB_MAX_WARPS2 22
+#endif
+constexpr int kMaxWarps2 = ACB_MAX_WARPS2;  // two segments per lane: twice the staging per warp, up to 88 registers
 constexpr int kChunk = 64;                // bytes per lane per stage
 constexpr int kRow = kChunk;              // a lane's row in the staging buffer; its 16-byte units are swizzled by (lane >> 1) & 3
-constexpr int kStageBytes = 32 * kRow;    // per warp per buffer
+constexpr int kStageBytes = 32 * kRow;    // per warp per buffer and per segment of a lane
 constexpr int kStageOffset = 256 + 128;   // column map + mbarrier slot, after the hot table
-constexpr int kMetaBytes = 32 * 8;        // per warp: (first 16-byte unit, chunk count) of each lane, read by the copy issue
+constexpr int kMetaBytes = 32 * 8;        // per warp and per segment of a lane: (first 16-byte unit, chunk count), read by the copy issue
 
 struct FastTab {
     uint32_t cmap;  // shared address of the byte -> column map (kColClass)
@@ -293,8 +297,8 @@ __device__ __forceinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &
     }
 }
 
-template <int MODE, bool CP, int COLMODE>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+template <int MODE, bool CP, int COLMODE, int V>
+__global__ void __launch_bounds__((V == 1 ? kMaxWarps : kMaxWarps2) * 32, 1)
 scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, SegInfo *seg_info, uint32_t H,
                    uint32_t hot_bytes, unsigned int *task_counter, unsigned long long *trap_stats) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -366,269 +370,354 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     auto row_of = [&](uint32_t addr) { return (addr - hot_s) / row_bytes; };
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t meta_s = stage_all_s + warp * kMetaBytes;
-    const uint32_t stage_s = stage_all_s + (blockDim.x >> 5) * kMetaBytes + warp * 2 * kStageBytes;
+    constexpr uint32_t kRows = 32 * V;                 // virtual lanes (segments) per warp-task
+    constexpr uint32_t kBufBytes = kRows * kRow;       // one staging buffer of a warp
+    constexpr uint32_t kWarpMeta = kRows * 8;
+    const uint32_t meta_s = stage_all_s + warp * kWarpMeta;
+    const uint32_t stage_s = stage_all_s + (blockDim.x >> 5) * kWarpMeta + warp * 2 * kBufBytes;
     const uintptr_t gbase = reinterpret_cast<uintptr_t>(B.bytes + P.origin);  // 64-byte aligned by construction of the plan
-    // copy instruction i of a stage moves 16-byte unit (lane & 3) of lane (i * 8 + lane / 4); the unit's
+    // copy instruction i of a stage moves 16-byte unit (lane & 3) of row (i * 8 + lane / 4); the unit's
     // place in its row is swizzled by (row >> 1) & 3, which does not depend on i
     const uint32_t cp_dst = stage_s + (lane >> 2) * kRow + (((lane & 3) ^ ((lane >> 3) & 3)) << 4);
     const uint32_t cp_meta = meta_s + (lane >> 2) * 8;
-    // this lane's own row: the address of its unit 0
+    // this lane's rows (virtual lanes lane, lane + 32, ...): the address of unit 0 of the first
     const uint32_t row_s = stage_s + lane * kRow + (((lane >> 1) & 3) << 4);
     const uint32_t q = P.lane_stride;
-    const uint32_t n_tasks = (uint32_t)(((uint64_t)P.n_segments + 32ull * q - 1) / (32ull * q) * q);
+    const uint32_t n_tasks = (uint32_t)(((uint64_t)P.n_segments + (uint64_t)kRows * q - 1) / ((uint64_t)kRows * q) * q);
+
+    // The exact scanner's state and the segment bookkeeping live in LOCAL memory on purpose (their
+    // addresses are laundered through an empty asm so the compiler cannot promote the ~28 words per
+    // segment to registers): only the careful path touches them, and the chunk loop needs the registers.
+    PieceCtx c_mem[V];
+    LaneSeg L_mem[V];
+    PieceCtx *c_ptr = c_mem;
+    LaneSeg *L_ptr = L_mem;
+    asm volatile("" : "+l"(c_ptr), "+l"(L_ptr));
 
     for (;;) {
-        // ---- claim the next warp-task: 32 segments, lane_stride apart -----------------
+        // ---- claim the next warp-task: 32 * V segments, lane_stride apart --------------
         unsigned int task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
         if (task >= n_tasks) break;
 
-        // The exact scanner's state and the segment bookkeeping live in LOCAL memory on purpose (their
-        // addresses are laundered through an empty asm so the compiler cannot promote the ~28 words to
-        // registers): only the careful path touches them, and the chunk loop needs the registers.
-        PieceCtx c_mem;
-        LaneSeg L_mem;
-        PieceCtx *c_ptr = &c_mem;
-        LaneSeg *L_ptr = &L_mem;
-        asm volatile("" : "+l"(c_ptr), "+l"(L_ptr));
-        PieceCtx &c = *c_ptr;
-        LaneSeg &L = *L_ptr;
-        L.seg = (int64_t)(((uint64_t)(task / q) * 32 + lane) * q + task % q);
-        L.done = 1;
-        L.spec_state = kNoState;
-        L.head_count = 0;
-        uint32_t off16 = 0, nchunks = 0;
-        uint32_t pos = 0, s = hot_s, stop = 0, cpd = 0;
-        bool warm = false;  // the current piece is the silent warm-up before the segment
-        const int64_t stream_lo = bounds[0], stream_hi = bounds[1];
-        const int64_t glo = P.origin + L.seg * (int64_t)P.seg_bytes;
-        const int64_t lo = max(glo, stream_lo), hi = min(glo + (int64_t)P.seg_bytes, stream_hi);
-        if (L.seg < P.n_segments && lo >= hi) {
-            // a segment outside the stream (the plan is sized from the buffer length): nothing to scan
-            uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
-            dst[0] = make_uint4(kNoState, kRoot, 0u, 0u);
-            dst[1] = make_uint4(0u, 0u, 0u, 0u);
-            out.unit_counts[2 * L.seg] = 0;
-            out.unit_counts[2 * L.seg + 1] = 0;
-        } else if (L.seg < P.n_segments) {
-            // the haystack containing lo: try the position an equal-length batch would put it at, else search
-            int64_t h = P.avg_len ? (lo - stream_lo) / (int64_t)P.avg_len : 0;
-            if (h >= B.n_haystacks) h = B.n_haystacks - 1;
-            int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);
-            if (!(hs <= lo && lo < he)) {
-                h = find_haystack(B, lo);
-                hs = __ldg(B.offsets + h);
-                he = __ldg(B.offsets + h + 1);
-            }
-            const bool cont = hs < lo;
-            const int64_t w = cont ? max(hs, lo - (int64_t)P.warm) : lo;
-            const uintptr_t pw = reinterpret_cast<uintptr_t>(B.bytes + w);
-            const uintptr_t a0 = pw & ~uintptr_t(kChunk - 1);
-            L.org = w - (int64_t)(pw - a0);
-            L.lo_rel = (uint32_t)(lo - L.org);
-            L.hi_rel = (uint32_t)(hi - L.org);
-            L.h = (uint32_t)h;
-            L.kind = cont ? kPieceWarm : kPieceNormal;
-            L.done = 0;
-            off16 = (uint32_t)((a0 - gbase) >> 4);
-            nchunks = (L.hi_rel + kChunk - 1) / kChunk;
-            c.base = B.bytes + L.org;
-            c.at = (uint32_t)(w - L.org);
-            c.limit = (uint32_t)(he - L.org);
-            c.stop = cont ? L.lo_rel : min(L.hi_rel, c.limit);
-            c.emit_from = cont ? 0xffffffffu : 0u;  // the warm-up reports nothing
-            c.state = kRoot;
-            c.have = 0;
-            c.last_pid = c.last_end = 0;
-            c.hay = (uint32_t)h;
-            c.hay_delta = (uint32_t)(L.org - hs);
-            c.unit = (uint32_t)(2 * L.seg + 1);
-            c.nemit = 0;
-            c.cp_pos = c.at;
-            c.cp_cont = 0;
-            warm = cont;
-            // the first piece is never empty (lo < hi, and a warm-up starts before lo) and starts in the
-            // root state, which is hot row 0: straight into the fast path
-            pos = c.at;
-            stop = c.stop;
-        }
-        bool done = L.done != 0;
-        if (done) nchunks = 0;
-        const uint32_t kmax = __reduce_max_sync(0xffffffffu, nchunks);
-        // where each lane's bytes are: read back by whichever lane copies them (no shuffles in the loop:
-        // the compiler cannot prove the warp converged there and would emit a slow collective path)
+        // per segment of this lane (compile-time indexed: registers)
+        uint32_t pos[V], s[V], stop[V], cpd[V];
+        bool done[V], warm[V];  // warm: the current piece is the silent warm-up before the segment
+        uint32_t nch_max = 0;
         __syncwarp();  // the previous task no longer reads meta / the staging buffers
-        sts64(meta_s + lane * 8, make_uint2(off16, nchunks));
+        const int64_t stream_lo = bounds[0], stream_hi = bounds[1];
+#pragma unroll
+        for (int t = 0; t < V; t++) {
+            PieceCtx &c = c_ptr[t];
+            LaneSeg &L = L_ptr[t];
+            L.seg = (int64_t)(((uint64_t)(task / q) * kRows + (uint32_t)t * 32u + lane) * q + task % q);
+            L.done = 1;
+            L.spec_state = kNoState;
+            L.head_count = 0;
+            uint32_t off16 = 0, nchunks = 0;
+            pos[t] = 0;
+            s[t] = hot_s;
+            stop[t] = 0;
+            cpd[t] = 0;
+            warm[t] = false;
+            const int64_t glo = P.origin + L.seg * (int64_t)P.seg_bytes;
+            const int64_t lo = max(glo, stream_lo), hi = min(glo + (int64_t)P.seg_bytes, stream_hi);
+            if (L.seg < P.n_segments && lo >= hi) {
+                // a segment outside the stream (the plan is sized from the buffer length): nothing to scan
+                uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
+                dst[0] = make_uint4(kNoState, kRoot, 0u, 0u);
+                dst[1] = make_uint4(0u, 0u, 0u, 0u);
+                out.unit_counts[2 * L.seg] = 0;
+                out.unit_counts[2 * L.seg + 1] = 0;
+            } else if (L.seg < P.n_segments) {
+                // the haystack containing lo: try the position an equal-length batch would put it at, else search
+                // (32-bit arithmetic: a buffer is shorter than 4 GiB)
+                int64_t h = P.avg_len ? (int64_t)((uint32_t)(lo - stream_lo) / (uint32_t)P.avg_len) : 0;
+                if (h >= B.n_haystacks) h = B.n_haystacks - 1;
+                int64_t hs = __ldg(B.offsets + h), he = __ldg(B.offsets + h + 1);
+                if (!(hs <= lo && lo < he)) {
+                    h = find_haystack(B, lo);
+                    hs = __ldg(B.offsets + h);
+                    he = __ldg(B.offsets + h + 1);
+                }
+                const bool cont = hs < lo;
+                const int64_t w = cont ? max(hs, lo - (int64_t)P.warm) : lo;
+                const uintptr_t pw = reinterpret_cast<uintptr_t>(B.bytes + w);
+                const uintptr_t a0 = pw & ~uintptr_t(kChunk - 1);
+                L.org = w - (int64_t)(pw - a0);
+                L.lo_rel = (uint32_t)(lo - L.org);
+                L.hi_rel = (uint32_t)(hi - L.org);
+                L.h = (uint32_t)h;
+                L.kind = cont ? kPieceWarm : kPieceNormal;
+                L.done = 0;
+                off16 = (uint32_t)((a0 - gbase) >> 4);
+                nchunks = (L.hi_rel + kChunk - 1) / kChunk;
+                c.base = B.bytes + L.org;
+                c.at = (uint32_t)(w - L.org);
+                c.limit = (uint32_t)(he - L.org);
+                c.stop = cont ? L.lo_rel : min(L.hi_rel, c.limit);
+                c.emit_from = cont ? 0xffffffffu : 0u;  // the warm-up reports nothing
+                c.state = kRoot;
+                c.have = 0;
+                c.last_pid = c.last_end = 0;
+                c.hay = (uint32_t)h;
+                c.hay_delta = (uint32_t)(L.org - hs);
+                c.unit = (uint32_t)(2 * L.seg + 1);
+                c.nemit = 0;
+                c.cp_pos = c.at;
+                c.cp_cont = 0;
+                warm[t] = cont;
+                // the first piece is never empty (lo < hi, and a warm-up starts before lo) and starts in the
+                // root state, which is hot row 0: straight into the fast path
+                pos[t] = c.at;
+                stop[t] = c.stop;
+            }
+            done[t] = L.done != 0;
+            if (done[t]) nchunks = 0;
+            nch_max = max(nch_max, nchunks);
+            // where each row's bytes are: read back by whichever lane copies them (no shuffles in the loop:
+            // the compiler cannot prove the warp converged there and would emit a slow collective path)
+            sts64(meta_s + ((uint32_t)t * 32u + lane) * 8, make_uint2(off16, nchunks));
+        }
+        const uint32_t kmax = __reduce_max_sync(0xffffffffu, nch_max);
         __syncwarp();
 
-        // stage chunk k into buffer BUF (compile-time: every shared-memory address below is base + immediate)
-        auto issue = [&](auto buf_tag, uint32_t k) {
-            constexpr uint32_t BUF = decltype(buf_tag)::value;
+        // stage chunk k of every row into buffer (k & 1)
+        auto issue = [&](uint32_t k) {
+            const uint32_t dst = cp_dst + (k & 1u) * kBufBytes;
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int i = 0; i < 4 * V; i++) {
                 const uint2 m = lds64(cp_meta + i * 64);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + ((size_t)(m.x + k * 4 + (lane & 3)) << 4);
-                cp_async16(cp_dst + BUF * kStageBytes + i * 8 * kRow, src, k < m.y ? 16u : 0u);
+                cp_async16(dst + i * 8 * kRow, src, k < m.y ? 16u : 0u);
             }
             cp_async_commit();
         };
-        // hand the lane over to the exact scanner at position `pos`, come back at the next fast-resume point
-        auto leave_fast = [&](uint32_t min_at) {
-            c.state = __ldg(hot_img.hot2full + row_of(s));
-            c.at = pos;
-            if (CP) {
-                c.cp_pos = pos;
-                c.cp_cont = cpd;
-            }
-            settle<MODE, CP>(c, L, im, B, out, seg_info, hm, min_at);
-            done = L.done != 0;
-            pos = c.at;
-            stop = c.stop;
-            warm = !done && L.kind == kPieceWarm;
-            if (!done) {
-                s = hot_s + (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
-                if (CP) {
-                    cp_catch_up(c, pos);
-                    cpd = c.cp_cont;
-                }
-            }
-        };
-        // the piece ended exactly where the fast path stands: the cheap, common transitions
-        // (warm-up -> head piece; end of the segment) without going through the exact scanner
-        auto piece_end_fast = [&]() -> bool {
-            if (warm) {
-                // arrived at the segment start in state s: that is the guess; scan the head piece from it
-                L.spec_state = __ldg(hot_img.hot2full + row_of(s));
-                L.kind = kPieceHead;
-                stop = min(L.hi_rel, c.limit);
-                c.stop = stop;
-                c.emit_from = 0;
-                cpd = 0;
-                warm = false;
-                return true;
-            }
-            if (stop == L.hi_rel) {
-                // end of the segment: write the summary
-                uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
-                const uint32_t nem = c.nemit;
-                dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + row_of(s)), 0u,
-                                    L.kind == kPieceHead ? nem : L.head_count);
-                dst[1] = make_uint4(0u, CP ? cpd : 0u, 0u, 0u);
-                out.unit_counts[2 * L.seg] = 0;
-                out.unit_counts[2 * L.seg + 1] = nem;
-                L.done = 1;
-                done = true;
-                return true;
-            }
-            return false;
-        };
 
-        // everything that is not a clean whole chunk: 16-byte groups, then single bytes (one instance of this code)
-        auto generic = [&](uint32_t relk, uint32_t row) {
+        // Everything that is not a clean whole chunk, for segment t of this lane: 16-byte groups, then single
+        // bytes; with tail set, what is left when the chunks are used up.  ONE instance of this code (t and
+        // the row are run-time values here): it contains the exact scanner.
+        auto careful = [&](uint32_t t, uint32_t relk, uint32_t row, bool tail) {
+            PieceCtx &c = c_ptr[t];
+            LaneSeg &L = L_ptr[t];
+            // this segment's fast-path state, by value (the arrays stay compile-time indexed)
+            uint32_t S = s[0], POS = pos[0], STOP = stop[0], CPD = cpd[0];
+            bool DONE = done[0], WARM = warm[0];
+#pragma unroll
+            for (int u = 1; u < V; u++)
+                if (t == (uint32_t)u) {
+                    S = s[u];
+                    POS = pos[u];
+                    STOP = stop[u];
+                    CPD = cpd[u];
+                    DONE = done[u];
+                    WARM = warm[u];
+                }
+            // hand the lane over to the exact scanner at position POS, come back at the next fast-resume point
+            auto leave_fast = [&](uint32_t min_at) {
+                c.state = __ldg(hot_img.hot2full + row_of(S));
+                c.at = POS;
+                if (CP) {
+                    c.cp_pos = POS;
+                    c.cp_cont = CPD;
+                }
+                settle<MODE, CP>(c, L, im, B, out, seg_info, hm, min_at);
+                DONE = L.done != 0;
+                POS = c.at;
+                STOP = c.stop;
+                WARM = !DONE && L.kind == kPieceWarm;
+                if (!DONE) {
+                    S = hot_s + (uint32_t)__ldg(hot_img.full2hot + c.state) * row_bytes;
+                    if (CP) {
+                        cp_catch_up(c, POS);
+                        CPD = c.cp_cont;
+                    }
+                }
+            };
+            // the piece ended exactly where the fast path stands: the cheap, common transitions
+            // (warm-up -> head piece; end of the segment) without going through the exact scanner
+            auto piece_end_fast = [&]() -> bool {
+                if (WARM) {
+                    // arrived at the segment start in state S: that is the guess; scan the head piece from it
+                    L.spec_state = __ldg(hot_img.hot2full + row_of(S));
+                    L.kind = kPieceHead;
+                    STOP = min(L.hi_rel, c.limit);
+                    c.stop = STOP;
+                    c.emit_from = 0;
+                    CPD = 0;
+                    WARM = false;
+                    return true;
+                }
+                if (STOP == L.hi_rel) {
+                    // end of the segment: write the summary
+                    uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
+                    const uint32_t nem = c.nemit;
+                    dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + row_of(S)), 0u,
+                                        L.kind == kPieceHead ? nem : L.head_count);
+                    dst[1] = make_uint4(0u, CP ? CPD : 0u, 0u, 0u);
+                    out.unit_counts[2 * L.seg] = 0;
+                    out.unit_counts[2 * L.seg + 1] = nem;
+                    L.done = 1;
+                    DONE = true;
+                    return true;
+                }
+                return false;
+            };
 #pragma unroll 1
-            for (int j = 0; j < 4; j++) {
+            for (int j = 0; j < (tail ? 1 : 4); j++) {
                 const uint32_t g = relk + j * 16;
-                if (done || pos < g || pos >= g + 16) continue;  // this lane is not inside this group
-                if (pos == g && g + 16 <= stop) {
-                    // a whole 16-byte group in the fast path
-                    const uint4 w = lds128(row_unit(row, (uint32_t)j));
-                    uint32_t t = fstep4<COLMODE>(s, w.x, ft);
-                    t = fstep4<COLMODE>(t, w.y, ft);
-                    t = fstep4<COLMODE>(t, w.z, ft);
-                    t = fstep4<COLMODE>(t, w.w, ft);
-                    if (t != trap) {
-                        s = t;
-                        pos += 16;
-                        if (CP) {
-                            if ((w.x | w.y | w.z | w.w) & 0x80808080u)
-                                cpd += cont_bytes(w.x) + cont_bytes(w.y) + cont_bytes(w.z) + cont_bytes(w.w);
+                if (!tail) {
+                    if (DONE || POS < g || POS >= g + 16) continue;  // this lane is not inside this group
+                    if (POS == g && g + 16 <= STOP) {
+                        // a whole 16-byte group in the fast path
+                        const uint4 w = lds128(row_unit(row, (uint32_t)j));
+                        uint32_t x = fstep4<COLMODE>(S, w.x, ft);
+                        x = fstep4<COLMODE>(x, w.y, ft);
+                        x = fstep4<COLMODE>(x, w.z, ft);
+                        x = fstep4<COLMODE>(x, w.w, ft);
+                        if (x != trap) {
+                            S = x;
+                            POS += 16;
+                            if (CP) {
+                                if ((w.x | w.y | w.z | w.w) & 0x80808080u)
+                                    CPD += cont_bytes(w.x) + cont_bytes(w.y) + cont_bytes(w.z) + cont_bytes(w.w);
+                            }
+                            continue;
                         }
-                        continue;
                     }
                 }
                 // byte by byte through the hot table (bytes from the staged row): piece boundaries,
                 // unaligned positions, and the group something happens in -- the exact scanner only
-                // gets the byte that left the hot set
-                while (!done && pos >= g && pos < g + 16) {
-                    uint32_t min_at = stop;
-                    if (pos >= stop) {
-                        if (pos == stop && piece_end_fast()) continue;
-                    } else {
-                        const uint32_t b = lds8(row_byte(row, pos - relk));
-                        const uint32_t t = fstep<COLMODE>(s, b, ft);
-                        if (t != trap) {
-                            s = t;
-                            pos++;
-                            if (CP) cpd += (b & 0xC0u) == 0x80u;
+                // gets the byte that left the hot set (tail: no staged bytes are left to look at)
+                while (!DONE && (tail || (POS >= g && POS < g + 16))) {
+                    uint32_t min_at = STOP;
+                    if (POS >= STOP) {
+                        if (POS == STOP && piece_end_fast()) continue;
+                    } else if (!tail) {
+                        const uint32_t b = lds8(row_byte(row, POS - relk));
+                        const uint32_t x = fstep<COLMODE>(S, b, ft);
+                        if (x != trap) {
+                            S = x;
+                            POS++;
+                            if (CP) CPD += (b & 0xC0u) == 0x80u;
                             continue;
                         }
                         atomicAdd(trap_stats + 1, 1ULL);  // how well the hot set fits the data: the host re-profiles when traps are frequent
-                        min_at = pos + 1;
+                        min_at = POS + 1;
                     }
-                    leave_fast(min_at);  // (the one call into the exact scanner inside the chunk loop)
+                    leave_fast(min_at);  // (the one place the exact scanner is entered from)
                 }
             }
-        };
-        using Buf0 = std::integral_constant<uint32_t, 0>;
-        using Buf1 = std::integral_constant<uint32_t, 1>;
-        // One chunk: the whole 64 bytes through the table with one trap check when the lane is in the clean
-        // middle of a piece, else (a piece boundary, an unaligned start, a trap) the careful path.  The careful
-        // path is a structured branch of this body, so the warp reconverges before the next chunk.
-        auto body = [&](auto buf_tag, uint32_t k) {
-            constexpr uint32_t BUF = decltype(buf_tag)::value;
-            cp_async_wait_all();
-            __syncwarp();
-            if (k + 1 < kmax) issue(std::integral_constant<uint32_t, 1 - BUF>{}, k + 1);
-            const uint32_t row = row_s + BUF * kStageBytes;
-            const uint32_t relk = k * kChunk;
-            if (!done && warm && pos == stop && pos == relk) piece_end_fast();  // the warm-up ended right at this chunk
-            if (!done && pos == relk && relk + kChunk <= stop) {
-                uint32_t t = s, hb = 0;
-                uint4 w = lds128(row);
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint4 wn = w;
-                    if (j < 3) wn = lds128(row_unit(row, (uint32_t)j + 1));  // in flight while unit j is scanned
-                    // (kColAscii: raw-byte indexing, no clamp, speculative.  A byte >= 128 would index past its
-                    // row -- into the next rows / the guard row, never outside the table -- and the result is
-                    // thrown away: the OR of all words tells afterwards whether that happened.)
-                    t = fstep4<COLMODE, false>(t, w.x, ft);
-                    t = fstep4<COLMODE, false>(t, w.y, ft);
-                    t = fstep4<COLMODE, false>(t, w.z, ft);
-                    t = fstep4<COLMODE, false>(t, w.w, ft);
-                    if (CP || COLMODE == kColAscii) hb |= w.x | w.y | w.z | w.w;
-                    w = wn;
+            for (int u = 0; u < V; u++)
+                if (t == (uint32_t)u) {
+                    s[u] = S;
+                    pos[u] = POS;
+                    stop[u] = STOP;
+                    cpd[u] = CPD;
+                    done[u] = DONE;
+                    warm[u] = WARM;
                 }
-                const bool high = (hb & 0x80808080u) != 0;
-                if (t != trap && !(COLMODE == kColAscii && high)) {
-                    s = t;
-                    pos += kChunk;
-                    if (CP && high) {
-                        // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
-                        // continuation bytes from the staged row again (do not keep 16 words live for this)
+        };
+
+        // One chunk: each of the lane's segments that is in the clean middle of a piece takes its whole 64 bytes
+        // through the table with one trap check -- the V dependent chains are independent of each other and
+        // interleave, hiding each other's shared-memory latency; whatever is not clean goes the careful way.
+        if (kmax) issue(0);
+        for (uint32_t k = 0; k <= kmax; k++) {
+            const bool tail = k == kmax;  // past the last chunk: whatever is left of the segments (normally just their summaries)
+            const uint32_t row0 = row_s + (k & 1u) * kBufBytes;
+            const uint32_t relk = k * kChunk;
+            if (!tail) {
+                cp_async_wait_all();
+                __syncwarp();
+                if (k + 1 < kmax) issue(k + 1);
+                bool clean[V], any_clean = false;
 #pragma unroll
-                        for (int j = 0; j < 4; j++) {
-                            const uint4 v = lds128(row_unit(row, (uint32_t)j));
-                            cpd += cont_bytes(v.x) + cont_bytes(v.y) + cont_bytes(v.z) + cont_bytes(v.w);
+                for (int t = 0; t < V; t++) {
+                    if (!done[t] && warm[t] && pos[t] == stop[t] && pos[t] == relk) {
+                        // the warm-up ended right at this chunk, in state s: that is the guess for the segment start;
+                        // the head piece is scanned from it (same as piece_end_fast in the careful path)
+                        PieceCtx &c = c_ptr[t];
+                        LaneSeg &L = L_ptr[t];
+                        L.spec_state = __ldg(hot_img.hot2full + row_of(s[t]));
+                        L.kind = kPieceHead;
+                        stop[t] = min(L.hi_rel, c.limit);
+                        c.stop = stop[t];
+                        c.emit_from = 0;
+                        cpd[t] = 0;
+                        warm[t] = false;
+                    }
+                    clean[t] = !done[t] && pos[t] == relk && relk + kChunk <= stop[t];
+                    any_clean |= clean[t];
+                }
+                if (any_clean) {
+                    // (a segment that is not clean runs along on whatever its row holds; the result is discarded)
+                    uint32_t x[V], hb[V];
+                    uint4 w[V];
+#pragma unroll
+                    for (int t = 0; t < V; t++) {
+                        x[t] = s[t];
+                        hb[t] = 0;
+                        w[t] = lds128(row0 + t * 32 * kRow);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint4 wn[V];
+#pragma unroll
+                        for (int t = 0; t < V; t++) {
+                            wn[t] = w[t];
+                            if (j < 3) wn[t] = lds128(row_unit(row0 + t * 32 * kRow, (uint32_t)j + 1));  // in flight while unit j is scanned
+                        }
+                        // (kColAscii: raw-byte indexing, no clamp, speculative.  A byte >= 128 would index past its
+                        // row -- into the next rows / the guard row, never outside the table -- and the result is
+                        // thrown away: the OR of all words tells afterwards whether that happened.)
+#pragma unroll
+                        for (int t = 0; t < V; t++) x[t] = fstep4<COLMODE, false>(x[t], w[t].x, ft);
+#pragma unroll
+                        for (int t = 0; t < V; t++) x[t] = fstep4<COLMODE, false>(x[t], w[t].y, ft);
+#pragma unroll
+                        for (int t = 0; t < V; t++) x[t] = fstep4<COLMODE, false>(x[t], w[t].z, ft);
+#pragma unroll
+                        for (int t = 0; t < V; t++) x[t] = fstep4<COLMODE, false>(x[t], w[t].w, ft);
+#pragma unroll
+                        for (int t = 0; t < V; t++) {
+                            if (CP || COLMODE == kColAscii) hb[t] |= w[t].x | w[t].y | w[t].z | w[t].w;
+                            w[t] = wn[t];
                         }
                     }
-                    return;
+#pragma unroll
+                    for (int t = 0; t < V; t++) {
+                        const bool high = (hb[t] & 0x80808080u) != 0;
+                        if (clean[t] && x[t] != trap && !(COLMODE == kColAscii && high)) {
+                            s[t] = x[t];
+                            pos[t] += kChunk;
+                            if (CP && high) {
+                                // multi-byte characters in this chunk (rare in mostly-ASCII text): count their
+                                // continuation bytes from the staged row again (do not keep 16 words live for this)
+#pragma unroll
+                                for (int j = 0; j < 4; j++) {
+                                    const uint4 v = lds128(row_unit(row0 + t * 32 * kRow, (uint32_t)j));
+                                    cpd[t] += cont_bytes(v.x) + cont_bytes(v.y) + cont_bytes(v.z) + cont_bytes(v.w);
+                                }
+                            }
+                        }
+                        // else: something happened in these 64 bytes (or, kColAscii, they hold high bytes); s and
+                        // pos are untouched and the careful path goes through them group by group
+                    }
                 }
-                // something happened in these 64 bytes (or, kColAscii, they hold high bytes); s and pos are
-                // untouched and the careful path goes through them group by group
             }
-            generic(relk, row);
-        };
-        if (kmax) issue(Buf0{}, 0);
-        for (uint32_t k = 0; k < kmax; k += 2) {
-            body(Buf0{}, k);
-            if (k + 1 < kmax) body(Buf1{}, k + 1);
-        }
-        // the end of the segment (normally reached in the fast path, right at its last byte)
-        while (!done) {
-            if (!(pos == stop && piece_end_fast())) leave_fast(stop);
+            // segments that still stand inside this chunk (tail: that are not finished); a structured branch, so the
+            // warp reconverges before the next chunk
+            uint32_t need = 0;
+#pragma unroll
+            for (int t = 0; t < V; t++) need |= (!done[t] && (tail || pos[t] < relk + kChunk)) ? (1u << t) : 0u;
+            if (need) {
+#pragma unroll 1
+                for (uint32_t t = 0; t < (uint32_t)V; t++)
+                    if (need & (1u << t)) careful(t, relk, row0 + t * 32 * kRow, tail);
+            }
         }
     }
 }

@@ -169,6 +169,7 @@ def main():
     ap.add_argument("--haystacks", type=int, default=N_HAY, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--segment-bytes", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--kernel", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--hot-rows", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--table", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
@@ -196,9 +197,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     L = _capi.lib()
-    if args.segment_bytes or args.hot_rows or args.table:
+    if args.segment_bytes or args.hot_rows or args.table or args.kernel:
         import ctypes
-        t = _capi.Tuning(0, args.hot_rows, args.segment_bytes, args.table)
+        t = _capi.Tuning(args.kernel, args.hot_rows, args.segment_bytes, args.table)
         L.acb_set_tuning(ctypes.byref(t))
     n_hay = args.haystacks
     # two different batches per rank (rank r owns haystack indices [r*2*n, (r+1)*2*n)): weak scaling

@@ -29,7 +29,7 @@ def set_kernel(kernel=0, hot_rows=0, segment_bytes=0, table=0):
 
 
 @pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments", "staged-compact-table",
-                        "staged-byte-table-tiny"])
+                        "staged-byte-table-tiny", "staged-two-per-lane", "staged-two-per-lane-tiny"])
 def kernel(request):
     if request.param == "plain":
         set_kernel(1)
@@ -41,6 +41,10 @@ def kernel(request):
         set_kernel(2, 0, 0, 1)        # column-indexed table even where the byte-indexed one would do
     elif request.param == "staged-byte-table-tiny":
         set_kernel(2, 7, 256, 2)      # byte-indexed table forced, 7 rows, 256-byte segments
+    elif request.param == "staged-two-per-lane":
+        set_kernel(3)                 # two segments per lane (two interleaved chains)
+    elif request.param == "staged-two-per-lane-tiny":
+        set_kernel(3, 6, 128, 1)      # ... with 6 hot rows and 128-byte segments: careful path and repair everywhere
     else:
         set_kernel(2, 0, 128)  # 128-byte segments: speculative starts and the repair pass everywhere
     yield request.param
