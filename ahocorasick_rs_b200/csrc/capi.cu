@@ -556,8 +556,8 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     const uint32_t row_bytes = COLMODE == kColAscii ? kAsciiCols * 2 : im.n_cols * 2;
     const uint32_t stage_bytes = (uint32_t)warps * V * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
-    if (budget < stage_bytes + kStageOffset + 3 * row_bytes + 128) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
-    uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / row_bytes;  // includes the trap row
+    if (budget < stage_bytes + kStageOffset + 3 * (row_bytes + 4) + 256) return fail(ACB_ECUDA, "not enough shared memory for the staged kernel");
+    uint32_t rows = (budget - stage_bytes - kStageOffset - 256) / (row_bytes + 4);  // includes the trap row; +4: the row's hot2full entry
     // table entries are 16-bit shared-memory ADDRESSES: the table (it starts dynamic shared memory) must end below 64 KB
     if (rows > (60u * 1024u) / row_bytes) rows = (60u * 1024u) / row_bytes;
     if (COLMODE == kColAscii) rows -= 1;                                        // ... and the guard row behind it
@@ -567,7 +567,7 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < H) H = (uint32_t)g_tuning.hot_rows;
     if (H < 1) return fail(ACB_ECUDA, "rows too wide for the staged kernel");
     const uint32_t hot_bytes = (((H + 1 + (COLMODE == kColAscii ? 1 : 0)) * row_bytes) + 127u) & ~127u;
-    const uint32_t smem = hot_bytes + kStageOffset + stage_bytes;
+    const uint32_t smem = hot_bytes + kStageOffset + (((H + 1) * 4 + 127u) & ~127u) + stage_bytes;
     CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
     kern<<<ctas, warps * 32, smem, st>>>(im, hot, B, P, out, seg_info, H, hot_bytes, task_counter, trap_stats);
     g_launches++;
@@ -579,7 +579,7 @@ uint32_t ascii_rows_that_fit(const DeviceInfo &d) {
     const uint32_t stage_bytes = (uint32_t)kMaxWarps * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
     if (budget < stage_bytes + kStageOffset + 128 + 2 * kAsciiCols * 2) return 0;
-    uint32_t rows = (budget - stage_bytes - kStageOffset - 128) / (kAsciiCols * 2);
+    uint32_t rows = (budget - stage_bytes - kStageOffset - 256) / (kAsciiCols * 2 + 4);
     if (rows > (60u * 1024u) / (kAsciiCols * 2)) rows = (60u * 1024u) / (kAsciiCols * 2);  // 16-bit row addresses
     return rows - 2;  // minus the trap row and the guard row
 }

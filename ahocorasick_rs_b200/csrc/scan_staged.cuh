@@ -99,6 +99,11 @@ __device__ __forceinline__ uint32_t lds8(uint32_t addr) {
     asm volatile("ld.shared.u8 %0, [%1];\n" : "=r"(v) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));  // (only used on tables that never change after the prologue)
+    return v;
+}
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     uint2 v;
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(v.x), "=r"(v.y) : "r"(addr));
@@ -305,7 +310,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     const uint32_t hot_s = (uint32_t)__cvta_generic_to_shared(smem);  // the table; also the address of hot row 0 (the root)
     const uint32_t cmap_s = hot_s + hot_bytes;                        // 256 B
     const uint32_t bar_s = cmap_s + 256;                              // mbarrier, then the stream bounds (2 x int64)
-    const uint32_t stage_all_s = cmap_s + kStageOffset;               // 128-aligned by construction
+    const uint32_t h2f_s = cmap_s + kStageOffset;                     // hot row -> automaton state, u32[H + 1] (the trap row maps to the dead state)
+    const uint32_t stage_all_s = h2f_s + (((H + 1) * 4 + 127u) & ~127u);  // 128-aligned by construction
     const uint32_t row_entries = COLMODE == kColAscii ? kAsciiCols : im.n_cols;
     const uint32_t row_bytes = row_entries * 2;
     const uint32_t trap_off = H * row_bytes;
@@ -354,6 +360,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     {
         uint16_t *h16 = reinterpret_cast<uint16_t *>(smem);
         for (uint32_t i = threadIdx.x; i < guard_entries; i += blockDim.x) h16[n_entries + i] = (uint16_t)trap;
+        uint32_t *h2f = reinterpret_cast<uint32_t *>(smem + hot_bytes + kStageOffset);
+        for (uint32_t i = threadIdx.x; i <= H; i += blockDim.x) h2f[i] = i < H ? __ldg(hot_img.hot2full + i) : kDead;
     }
     __syncthreads();
     // 16-byte groups scanned, for the host's traps-per-group statistic (it re-profiles when traps are frequent)
@@ -368,6 +376,9 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     ft.maxc = im.n_cols - 1;
     // hot row index <-> row address
     auto row_of = [&](uint32_t addr) { return (addr - hot_s) / row_bytes; };
+    // the automaton state of a hot row, from the shared-memory copy of hot2full (no global round trip on the
+    // segment-end and warm-up-end paths)
+    auto state_of = [&](uint32_t addr) { return lds32(h2f_s + row_of(addr) * 4); };
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr uint32_t kRows = 32 * V;                 // virtual lanes (segments) per warp-task
@@ -396,6 +407,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
 
     for (;;) {
         // ---- claim the next warp-task: 32 * V segments, lane_stride apart --------------
+        // (claiming one task ahead to hide the atomic's latency was measured: it is slower, because a task
+        // claimed early by a busy warp cannot be taken by an idle one at the end of the kernel)
         unsigned int task = 0;
         if (lane == 0) task = atomicAdd(task_counter, 1u);
         task = __shfl_sync(0xffffffffu, task, 0);
@@ -403,6 +416,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
 
         // per segment of this lane (compile-time indexed: registers)
         uint32_t pos[V], s[V], stop[V], cpd[V];
+        uint32_t hi_rel[V], stop_head[V];  // the segment end, and where the head piece (after the warm-up) stops
         bool done[V], warm[V];  // warm: the current piece is the silent warm-up before the segment
         uint32_t nch_max = 0;
         __syncwarp();  // the previous task no longer reads meta / the staging buffers
@@ -421,6 +435,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             stop[t] = 0;
             cpd[t] = 0;
             warm[t] = false;
+            hi_rel[t] = stop_head[t] = 0;
             const int64_t glo = P.origin + L.seg * (int64_t)P.seg_bytes;
             const int64_t lo = max(glo, stream_lo), hi = min(glo + (int64_t)P.seg_bytes, stream_hi);
             if (L.seg < P.n_segments && lo >= hi) {
@@ -472,6 +487,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                 // root state, which is hot row 0: straight into the fast path
                 pos[t] = c.at;
                 stop[t] = c.stop;
+                hi_rel[t] = L.hi_rel;
+                stop_head[t] = min(L.hi_rel, c.limit);
             }
             done[t] = L.done != 0;
             if (done[t]) nchunks = 0;
@@ -502,7 +519,7 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             PieceCtx &c = c_ptr[t];
             LaneSeg &L = L_ptr[t];
             // this segment's fast-path state, by value (the arrays stay compile-time indexed)
-            uint32_t S = s[0], POS = pos[0], STOP = stop[0], CPD = cpd[0];
+            uint32_t S = s[0], POS = pos[0], STOP = stop[0], CPD = cpd[0], HI = hi_rel[0], HEAD = stop_head[0];
             bool DONE = done[0], WARM = warm[0];
 #pragma unroll
             for (int u = 1; u < V; u++)
@@ -511,12 +528,14 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                     POS = pos[u];
                     STOP = stop[u];
                     CPD = cpd[u];
+                    HI = hi_rel[u];
+                    HEAD = stop_head[u];
                     DONE = done[u];
                     WARM = warm[u];
                 }
             // hand the lane over to the exact scanner at position POS, come back at the next fast-resume point
             auto leave_fast = [&](uint32_t min_at) {
-                c.state = __ldg(hot_img.hot2full + row_of(S));
+                c.state = state_of(S);
                 c.at = POS;
                 if (CP) {
                     c.cp_pos = POS;
@@ -540,24 +559,24 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             auto piece_end_fast = [&]() -> bool {
                 if (WARM) {
                     // arrived at the segment start in state S: that is the guess; scan the head piece from it
-                    L.spec_state = __ldg(hot_img.hot2full + row_of(S));
+                    L.spec_state = state_of(S);
                     L.kind = kPieceHead;
-                    STOP = min(L.hi_rel, c.limit);
+                    STOP = HEAD;
                     c.stop = STOP;
                     c.emit_from = 0;
                     CPD = 0;
                     WARM = false;
                     return true;
                 }
-                if (STOP == L.hi_rel) {
-                    // end of the segment: write the summary
-                    uint4 *dst = reinterpret_cast<uint4 *>(seg_info + L.seg);
-                    const uint32_t nem = c.nemit;
-                    dst[0] = make_uint4(L.spec_state, __ldg(hot_img.hot2full + row_of(S)), 0u,
-                                        L.kind == kPieceHead ? nem : L.head_count);
+                if (STOP == HI) {
+                    // end of the segment: write the summary (everything it needs from local memory is read
+                    // first, in one batch: the stores below would otherwise force re-reads)
+                    const int64_t seg = L.seg;
+                    const uint32_t nem = c.nemit, spec = L.spec_state, kind = L.kind, hc = L.head_count;
+                    uint4 *dst = reinterpret_cast<uint4 *>(seg_info + seg);
+                    dst[0] = make_uint4(spec, state_of(S), 0u, kind == kPieceHead ? nem : hc);
                     dst[1] = make_uint4(0u, CP ? CPD : 0u, 0u, 0u);
-                    out.unit_counts[2 * L.seg] = 0;
-                    out.unit_counts[2 * L.seg + 1] = nem;
+                    *reinterpret_cast<uint2 *>(out.unit_counts + 2 * seg) = make_uint2(0u, nem);
                     L.done = 1;
                     DONE = true;
                     return true;
@@ -641,9 +660,9 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                         // the head piece is scanned from it (same as piece_end_fast in the careful path)
                         PieceCtx &c = c_ptr[t];
                         LaneSeg &L = L_ptr[t];
-                        L.spec_state = __ldg(hot_img.hot2full + row_of(s[t]));
+                        L.spec_state = state_of(s[t]);
                         L.kind = kPieceHead;
-                        stop[t] = min(L.hi_rel, c.limit);
+                        stop[t] = stop_head[t];
                         c.stop = stop[t];
                         c.emit_from = 0;
                         cpd[t] = 0;
