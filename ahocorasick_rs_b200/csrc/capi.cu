@@ -5,6 +5,7 @@
 #include <string>
 #include <utility>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include <cooperative_groups.h>
@@ -538,21 +539,9 @@ int launch_staged(const DevImage &im, const DevHot &hot, const Batch &B, const S
     const int ctas = d.sms;
     int warps = (int)((tasks + ctas - 1) / ctas);
     if (warps < 4) warps = 4;
-#ifndef ACB_BALANCE
-#define ACB_BALANCE 1
-#endif
-    if (warps > kWarpsMax && !ACB_BALANCE) warps = kWarpsMax;
-    if (warps > kWarpsMax) {
-        // every warp runs ceil(tasks / warps) tasks in the worst case: of the CTA sizes near the maximum take
-        // the one that wastes the least of its last round (12 500 tasks: 32 warps -> 2.64 tasks per warp,
-        // 88 % busy; 29 warps -> 2.91, 97 %)
-        double best = 0;
-        for (int w = kWarpsMax; w >= kWarpsMax - 4; w--) {
-            const double per = (double)tasks / ((double)ctas * w);
-            const double eff = per / std::ceil(per) * (1.0 - 0.01 * (kWarpsMax - w));
-            if (eff > best + 1e-9) best = eff, warps = w;
-        }
-    }
+    // as many warps as fit: the scan is a chain of dependent shared-memory loads per lane, more warps hide more of
+    // it (measured 26 -> 32 warps: 170 -> 164 us); balancing the last round of tasks instead was not better
+    if (warps > kWarpsMax) warps = kWarpsMax;
     const uint32_t row_bytes = COLMODE == kColAscii ? kAsciiCols * 2 : im.n_cols * 2;
     const uint32_t stage_bytes = (uint32_t)warps * V * (2 * kStageBytes + kMetaBytes);
     const uint32_t budget = (uint32_t)d.max_smem_optin;
@@ -717,10 +706,11 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         uint32_t fit128 = ascii_rows_that_fit(d);
         if (fit128 > hot.n_rows128) fit128 = hot.n_rows128;
         if (g_tuning.hot_rows > 0 && (uint32_t)g_tuning.hot_rows < fit128) fit128 = (uint32_t)g_tuning.hot_rows;
-        // Opt-in.  Measured on the config-2 text (about 1 chunk in 5 holds a multi-byte character and is
-        // scanned twice in this mode) it loses to the compact table: the kernel is bound by the issue rate
-        // of shared-memory loads, one per byte either way, not by the column arithmetic this saves.
-        const bool ascii = g_tuning.table == 2 && fit128 > 0;
+        // Byte-indexed (128-wide) rows make the transition two instructions per byte (IDP4A + LDS) instead of four,
+        // but they are 256 bytes each (only ~230 fit below 64 KB) and on the config-2 text the kernel is bound by
+        // the shared-memory pipe, not by instruction issue: measured equal to the compact table (162 vs 160 us).
+        // Opt-in (tuning.table = 2), one segment per lane only (two per lane leave too little room for the rows).
+        const bool ascii = g_tuning.table == 2 && fit128 > 0 && per_lane == 1;
         // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
         // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
         P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);

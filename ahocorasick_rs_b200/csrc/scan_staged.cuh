@@ -128,11 +128,35 @@ __device__ __forceinline__ uint32_t fstep(uint32_t s, uint32_t b, const FastTab 
         col = lds_tab_u8(f.cmap + b);
     else
         col = CLAMP ? min(b, 127u) : b;
-    return lds_tab(s + col + col);
+    // row + 2 * column as an IMAD: the kernel is bound by the ALU pipe (half rate; the byte extract and the
+    // column clamp live there), the multiply-add pipe is idle
+    uint32_t addr;
+    asm("mad.lo.u32 %0, %1, 2, %2;\n" : "=r"(addr) : "r"(col), "r"(s));
+    return lds_tab(addr);
+}
+
+// byte-indexed table: row + 2 * byte k of w in ONE instruction (IDP4A: w . (2 << 8k) + row), no byte extract
+template <uint32_t K>
+__device__ __forceinline__ uint32_t fstep_dp(uint32_t s, uint32_t w) {
+    uint32_t addr;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;\n" : "=r"(addr) : "r"(w), "r"(2u << (8 * K)), "r"(s));
+    return lds_tab(addr);
+}
+// bytes >= 0x80 of a word -> 0x7f (the byte-indexed table's "any other byte" column)
+__device__ __forceinline__ uint32_t clamp7f(uint32_t w) {
+    const uint32_t hi = w & 0x80808080u;
+    return (w | (hi - (hi >> 7))) & ~hi;
 }
 
 template <int COLMODE, bool CLAMP = true>
 __device__ __forceinline__ uint32_t fstep4(uint32_t s, uint32_t w, const FastTab &f) {
+    if (COLMODE == kColAscii && !CLAMP) {
+        // the caller has clamped the word's bytes to 0..127 already
+        s = fstep_dp<0>(s, w);
+        s = fstep_dp<1>(s, w);
+        s = fstep_dp<2>(s, w);
+        return fstep_dp<3>(s, w);
+    }
     s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4440), f);
     s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4441), f);
     s = fstep<COLMODE, CLAMP>(s, __byte_perm(w, 0, 0x4442), f);
@@ -405,13 +429,14 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
     LaneSeg *L_ptr = L_mem;
     asm volatile("" : "+l"(c_ptr), "+l"(L_ptr));
 
+    // Warp-tasks (32 * V segments, lane_stride apart) come from an atomic counter.  The claim for the NEXT task
+    // is issued when the last chunk of the current one starts: the atomic's round trip overlaps that chunk,
+    // and the first bytes of the next task are pulled towards L2 meanwhile.  (Claiming a whole task ahead was
+    // measured and is slower: a task claimed early by a busy warp cannot be taken by an idle one at the end.)
+    unsigned int claimed = 0;
+    if (lane == 0) claimed = atomicAdd(task_counter, 1u);
     for (;;) {
-        // ---- claim the next warp-task: 32 * V segments, lane_stride apart --------------
-        // (claiming one task ahead to hide the atomic's latency was measured: it is slower, because a task
-        // claimed early by a busy warp cannot be taken by an idle one at the end of the kernel)
-        unsigned int task = 0;
-        if (lane == 0) task = atomicAdd(task_counter, 1u);
-        task = __shfl_sync(0xffffffffu, task, 0);
+        const unsigned int task = __shfl_sync(0xffffffffu, claimed, 0);
         if (task >= n_tasks) break;
 
         // per segment of this lane (compile-time indexed: registers)
@@ -643,7 +668,10 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         // One chunk: each of the lane's segments that is in the clean middle of a piece takes its whole 64 bytes
         // through the table with one trap check -- the V dependent chains are independent of each other and
         // interleave, hiding each other's shared-memory latency; whatever is not clean goes the careful way.
-        if (kmax) issue(0);
+        if (kmax)
+            issue(0);
+        else if (lane == 0)
+            claimed = atomicAdd(task_counter, 1u);  // nothing to scan in this task (segments outside the stream)
         for (uint32_t k = 0; k <= kmax; k++) {
             const bool tail = k == kmax;  // past the last chunk: whatever is left of the segments (normally just their summaries)
             const uint32_t row0 = row_s + (k & 1u) * kBufBytes;
@@ -651,7 +679,11 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
             if (!tail) {
                 cp_async_wait_all();
                 __syncwarp();
-                if (k + 1 < kmax) issue(k + 1);
+                if (k + 1 < kmax) {
+                    issue(k + 1);
+                } else if (lane == 0) {
+                    claimed = atomicAdd(task_counter, 1u);  // the last chunk: fetch the next task meanwhile
+                }
                 bool clean[V], any_clean = false;
 #pragma unroll
                 for (int t = 0; t < V; t++) {
@@ -689,9 +721,20 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                             wn[t] = w[t];
                             if (j < 3) wn[t] = lds128(row_unit(row0 + t * 32 * kRow, (uint32_t)j + 1));  // in flight while unit j is scanned
                         }
-                        // (kColAscii: raw-byte indexing, no clamp, speculative.  A byte >= 128 would index past its
-                        // row -- into the next rows / the guard row, never outside the table -- and the result is
-                        // thrown away: the OR of all words tells afterwards whether that happened.)
+#pragma unroll
+                        for (int t = 0; t < V; t++) {
+                            if (CP || COLMODE == kColAscii) hb[t] |= w[t].x | w[t].y | w[t].z | w[t].w;
+                            if (COLMODE == kColAscii) {
+                                // byte-indexed table: bytes >= 0x80 (rare in mostly-ASCII text) are folded onto column 127
+                                // here, word-wise and only in the units that have any, so the chain needs no per-byte clamp
+                                if ((w[t].x | w[t].y | w[t].z | w[t].w) & 0x80808080u) {
+                                    w[t].x = clamp7f(w[t].x);
+                                    w[t].y = clamp7f(w[t].y);
+                                    w[t].z = clamp7f(w[t].z);
+                                    w[t].w = clamp7f(w[t].w);
+                                }
+                            }
+                        }
 #pragma unroll
                         for (int t = 0; t < V; t++) x[t] = fstep4<COLMODE, false>(x[t], w[t].x, ft);
 #pragma unroll
@@ -701,15 +744,12 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
 #pragma unroll
                         for (int t = 0; t < V; t++) x[t] = fstep4<COLMODE, false>(x[t], w[t].w, ft);
 #pragma unroll
-                        for (int t = 0; t < V; t++) {
-                            if (CP || COLMODE == kColAscii) hb[t] |= w[t].x | w[t].y | w[t].z | w[t].w;
-                            w[t] = wn[t];
-                        }
+                        for (int t = 0; t < V; t++) w[t] = wn[t];
                     }
 #pragma unroll
                     for (int t = 0; t < V; t++) {
                         const bool high = (hb[t] & 0x80808080u) != 0;
-                        if (clean[t] && x[t] != trap && !(COLMODE == kColAscii && high)) {
+                        if (clean[t] && x[t] != trap) {
                             s[t] = x[t];
                             pos[t] += kChunk;
                             if (CP && high) {
@@ -722,8 +762,8 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
                                 }
                             }
                         }
-                        // else: something happened in these 64 bytes (or, kColAscii, they hold high bytes); s and
-                        // pos are untouched and the careful path goes through them group by group
+                        // else: something happened in these 64 bytes; s and pos are untouched and the careful path
+                        // goes through them group by group
                     }
                 }
             }

@@ -29,16 +29,18 @@ def set_kernel(kernel=0, hot_rows=0, segment_bytes=0, table=0):
 
 
 @pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments", "staged-compact-table",
-                        "staged-byte-table-tiny", "staged-two-per-lane", "staged-two-per-lane-tiny"])
+                        "staged-byte-table", "staged-byte-table-tiny", "staged-two-per-lane", "staged-two-per-lane-tiny"])
 def kernel(request):
     if request.param == "plain":
         set_kernel(1)
     elif request.param == "staged":
-        set_kernel(2)                 # auto: byte-indexed table when the patterns are ASCII and the hot rows fit
+        set_kernel(2)                 # the default: compact (column-indexed) table, one segment per lane
     elif request.param == "staged-tiny-hot":
         set_kernel(2, 5, 0, 1)        # 5 hot rows, compact table: nearly every group leaves the hot set
     elif request.param == "staged-compact-table":
         set_kernel(2, 0, 0, 1)        # column-indexed table even where the byte-indexed one would do
+    elif request.param == "staged-byte-table":
+        set_kernel(2, 0, 0, 2)        # byte-indexed table (IDP4A transitions) wherever the patterns are ASCII
     elif request.param == "staged-byte-table-tiny":
         set_kernel(2, 7, 256, 2)      # byte-indexed table forced, 7 rows, 256-byte segments
     elif request.param == "staged-two-per-lane":
