@@ -103,13 +103,29 @@ __device__ __forceinline__ unsigned long long block_exclusive_scan(unsigned long
     return before + x - v;
 }
 
-// in[i * stride] for i in [0, n); one tile
-__device__ __forceinline__ void tile_sum_body(const uint32_t *in, uint32_t stride, uint64_t n, unsigned long long *tile_sums, uint64_t tile) {
+// item i = in[i * stride] (+ in[i * stride + 1] when PAIR: the two slots of a segment) for i in [0, n); one tile.
+// dense != null: the items are also written there, packed (a strided source is read only once that way).
+template <bool PAIR>
+__device__ __forceinline__ unsigned long long scan_item(const uint32_t *in, uint32_t stride, uint64_t i) {
+    if (PAIR) {
+        const uint2 v = *reinterpret_cast<const uint2 *>(in + i * stride);
+        return (unsigned long long)v.x + v.y;
+    }
+    return in[i * stride];
+}
+
+template <bool PAIR>
+__device__ __forceinline__ void tile_sum_body(const uint32_t *in, uint32_t stride, uint64_t n, unsigned long long *tile_sums, uint64_t tile,
+                                              uint32_t *dense) {
     const uint64_t base = tile * kScanTile + (uint64_t)threadIdx.x * kScanItems;
     unsigned long long v = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++)
-        if (base + i < n) v += in[(base + i) * stride];
+        if (base + i < n) {
+            const unsigned long long x = scan_item<PAIR>(in, stride, base + i);
+            if (dense) dense[base + i] = (uint32_t)x;
+            v += x;
+        }
     unsigned long long total;
     block_exclusive_scan(v, &total);
     if (threadIdx.x == 0) tile_sums[tile] = total;
@@ -125,6 +141,7 @@ __device__ __forceinline__ unsigned long long tile_prefix(const unsigned long lo
     return total;
 }
 
+template <bool PAIR>
 __device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t stride, uint64_t n, const unsigned long long *tile_sums,
                                                 unsigned long long *out, uint64_t tile) {
     const unsigned long long tile_start = tile_prefix(tile_sums, tile);
@@ -132,7 +149,7 @@ __device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t str
     unsigned long long vals[kScanItems], v = 0;
 #pragma unroll
     for (int i = 0; i < kScanItems; i++) {
-        vals[i] = base + i < n ? in[(base + i) * stride] : 0;
+        vals[i] = base + i < n ? scan_item<PAIR>(in, stride, base + i) : 0;
         v += vals[i];
     }
     unsigned long long total;
@@ -145,7 +162,6 @@ __device__ __forceinline__ void tile_apply_body(const uint32_t *in, uint32_t str
     }
 }
 
-
 // ---------------------------------------------------------------------------
 // final placement: raw match i of unit u with rank r goes to unit_offsets[u] + r
 // (segments: minus the matches the repair pass superseded); code point fix-up
@@ -155,7 +171,8 @@ struct OrderArgs {
     const uint32_t *raw_seq, *raw_unit, *raw_aux;
     unsigned long long raw_cap;
     const unsigned long long *raw_total;
-    const unsigned long long *unit_offsets;
+    const unsigned long long *unit_offsets;  // segments: one entry per SEGMENT (slot 0 first, then slot 1); else per unit
+    const uint32_t *unit_counts;
     const SegInfo *seg_info;             // null: units are haystacks (plain kernel)
     const unsigned long long *cont_cum;  // exclusive prefix sum of SegInfo.cont_tail (code points + segments)
     const int64_t *hay_offsets;
@@ -179,7 +196,9 @@ __device__ __forceinline__ void order_body(const OrderArgs &A) {
             if (seq < drop) continue;  // superseded by the repair pass
             seq -= drop;
         }
-        const unsigned long long dst = A.unit_offsets[u] + seq;
+        // a segment's slot-1 matches (the scan kernel's) come after its slot-0 matches (the repair pass's)
+        const unsigned long long dst =
+            A.seg_info ? A.unit_offsets[u >> 1] + ((u & 1u) ? A.unit_counts[u & ~1u] : 0u) + seq : A.unit_offsets[u] + seq;
         if (dst >= A.out_cap) continue;
         uint4 r = reinterpret_cast<const uint4 *>(A.raw)[i];  // haystack, pattern, start, end (bytes)
         if (A.codepoints) {
@@ -242,6 +261,7 @@ struct EpilogueArgs {
     const uint32_t *cont_tail;  // null: no code point prefix needed
     uint64_t n_segments;
     unsigned long long *cont_tiles, *cont_cum;
+    uint32_t *cont_dense;  // packed copy of SegInfo.cont_tail
     OrderArgs order;
     unsigned long long *match_offsets;
     unsigned int *need_repair;  // zeroed with the totals; set when a speculated segment start was wrong
@@ -252,11 +272,21 @@ template <int MODE, bool CP>
 __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    const uint64_t tiles = (E.n_units + kScanTile - 1) / kScanTile;
+    // segments: one scan item per segment (its two slots summed); plain kernel: one per haystack
+    const bool pairs = E.order.seg_info != nullptr;
+    const uint64_t n_items = pairs ? E.n_units / 2 : E.n_units;
+    const uint64_t tiles = (n_items + kScanTile - 1) / kScanTile;
     const uint64_t ctiles = E.cont_tail ? (E.n_segments + kScanTile - 1) / kScanTile : 0;
     auto sums = [&]() {
-        for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_sum_body(E.unit_counts, 1, E.n_units, E.tile_sums, t);
-        for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_sum_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, t);
+        // (one tile space for both arrays, so that different blocks take the count tiles and the tail tiles)
+        for (uint64_t tt = blockIdx.x; tt < tiles + ctiles; tt += gridDim.x) {
+            if (tt >= tiles)  // SegInfo.cont_tail sits at a 32-byte stride: read it once, keep a packed copy for the second pass
+                tile_sum_body<false>(E.cont_tail, 8, E.n_segments, E.cont_tiles, tt - tiles, E.cont_dense);
+            else if (pairs)
+                tile_sum_body<true>(E.unit_counts, 2, n_items, E.tile_sums, tt, nullptr);
+            else
+                tile_sum_body<false>(E.unit_counts, 1, n_items, E.tile_sums, tt, nullptr);
+        }
     };
     // phase 1: tile sums of the counts as the scan kernel left them, and -- non-overlapping searches -- the check of
     // every speculated segment start against the state its predecessor ended in (repair.cuh has the same rule)
@@ -280,13 +310,19 @@ __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) 
         grid.sync();
     }
     // phase 2: exclusive prefix sums (every block derives its tile's start from the tile sums)
-    for (uint64_t t = blockIdx.x; t < tiles; t += gridDim.x) tile_apply_body(E.unit_counts, 1, E.n_units, E.tile_sums, E.unit_offsets, t);
-    for (uint64_t t = blockIdx.x; t < ctiles; t += gridDim.x) tile_apply_body(E.cont_tail, 8, E.n_segments, E.cont_tiles, E.cont_cum, t);
+    for (uint64_t tt = blockIdx.x; tt < tiles + ctiles; tt += gridDim.x) {
+        if (tt >= tiles)
+            tile_apply_body<false>(E.cont_dense, 1, E.n_segments, E.cont_tiles, E.cont_cum, tt - tiles);
+        else if (pairs)
+            tile_apply_body<true>(E.unit_counts, 2, n_items, E.tile_sums, E.unit_offsets, tt);
+        else
+            tile_apply_body<false>(E.unit_counts, 1, n_items, E.tile_sums, E.unit_offsets, tt);
+    }
     grid.sync();
     // phase 3: ordered output; phase 4: per-haystack offsets into it
     order_body(E.order);
     grid.sync();
-    match_offsets_body(E.order.out, E.unit_offsets, E.n_units, E.totals, E.order.raw_cap, E.order.out_cap, E.B.n_haystacks,
+    match_offsets_body(E.order.out, E.unit_offsets, n_items, E.totals, E.order.raw_cap, E.order.out_cap, E.B.n_haystacks,
                        E.match_offsets);
 }
 
@@ -451,8 +487,8 @@ int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_
     plan->n_units = seg_units > n_haystacks ? seg_units : n_haystacks;
     if (plan->n_units < 1) plan->n_units = 1;
     const uint64_t tiles = (plan->n_units + kScanTile - 1) / kScanTile;
-    // [0] task counter | unit tile sums | cont tile sums | cont_cum (n_segments + 1)
-    plan->scratch_words = 2 + (tiles + 1) + (tiles + 1) + plan->n_segments + 2;
+    // [0] task counter, repair flag | unit tile sums | cont tile sums | cont_cum (n_segments + 1) | packed cont tails (u32)
+    plan->scratch_words = 2 + (tiles + 1) + (tiles + 1) + (plan->n_segments + 2) + (plan->n_segments / 2 + 2);
     return ACB_OK;
 }
 
@@ -741,6 +777,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
     unsigned long long *cont_tiles = tile_sums + max_tiles + 1;
     unsigned long long *cont_cum = cont_tiles + max_tiles + 1;
+    uint32_t *cont_dense = reinterpret_cast<uint32_t *>(cont_cum + plan->n_segments + 2);
     OrderArgs A;
     A.raw = ws->dev_raw;
     A.raw_seq = ws->dev_raw_seq;
@@ -749,6 +786,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     A.raw_cap = ws->raw_capacity;
     A.raw_total = totals + 4;
     A.unit_offsets = unit_offsets;
+    A.unit_counts = ws->dev_unit_counts;
     A.seg_info = segments ? seg_info : nullptr;
     A.cont_cum = cont_cum;
     A.hay_offsets = dev_offsets;
@@ -773,6 +811,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     E.n_segments = plan->n_segments;
     E.cont_tiles = cont_tiles;
     E.cont_cum = cont_cum;
+    E.cont_dense = cont_dense;
     E.order = A;
     E.match_offsets = match_offsets;
     E.need_repair = task_counter + 1;
