@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libacb200.so")
 SOURCES = ["capi.cu", "automaton.cpp"]
-HEADERS = ["automaton.h", "scan_core.cuh", "scan_staged.cuh", "repair.cuh", os.path.join("..", "..", "include", "acb200.h")]
+HEADERS = ["automaton.h", "scan_core.cuh", "scan_staged.cuh", "scan_global.cuh", "repair.cuh", os.path.join("..", "..", "include", "acb200.h")]
 
 
 def _stale() -> bool:

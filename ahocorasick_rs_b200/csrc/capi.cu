@@ -12,6 +12,7 @@
 
 #include "repair.cuh"
 #include "scan_staged.cuh"
+#include "scan_global.cuh"
 
 namespace acb {
 
@@ -623,6 +624,18 @@ int launch_staged_cols(const ImageHeader &h, const DevImage &im, const DevHot &h
 }
 
 template <int MODE, bool CP>
+int launch_global(const DevImage &im, const Batch &B, const SegPlan &P, const Sink &out, SegInfo *seg_info, const DeviceInfo &d,
+                  cudaStream_t st) {
+    int64_t blocks = (P.n_segments + 255) / 256;
+    const int64_t cap = (int64_t)d.sms * 64;  // grid-stride beyond that
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    scan_global_kernel<MODE, CP><<<(unsigned)blocks, 256, 0, st>>>(im, B, P, out, seg_info);
+    g_launches++;
+    return ACB_OK;
+}
+
+template <int MODE, bool CP>
 int launch_epilogue(EpilogueArgs &E, const DeviceInfo &d, cudaStream_t st) {
     auto kern = epilogue_kernel<MODE, CP>;
     static thread_local int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
@@ -719,8 +732,10 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
 
     int kernel = g_tuning.kernel;
     if (kernel == 0) kernel = 2;
-    if (!dev_hot || !hot_desc) kernel = 1;  // no hot image: the plain kernel (table in global memory / L2)
-    const bool segments = kernel == 2 || kernel == 3;
+    // the caller's profile says the hot rows do not cover this data: scan from the image in global memory / L2
+    if (kernel == 2 && g_tuning.kernel == 0 && hot_desc && (hot_desc->reserved & 1u)) kernel = 4;
+    if ((!dev_hot || !hot_desc) && kernel != 4) kernel = 1;  // no hot image: the plain kernel (one thread per haystack)
+    const bool segments = kernel == 2 || kernel == 3 || kernel == 4;
     const int per_lane = kernel == 3 ? 2 : 1;  // segments per lane of the staged kernel (3: two interleaved chains)
     SegPlan P{};
     uint64_t n_units = (uint64_t)n_haystacks;
@@ -736,6 +751,25 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
      : mode == kModeLeftmost ? (cp ? FN<kModeLeftmost, true>(__VA_ARGS__) : FN<kModeLeftmost, false>(__VA_ARGS__)) \
                              : (cp ? FN<kModeOverlap, true>(__VA_ARGS__) : FN<kModeOverlap, false>(__VA_ARGS__)))
     if (segments) {
+        // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
+        // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
+        P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);
+        P.seg_bytes = plan->segment_bytes;
+        P.warm = plan->warm_bytes;
+        P.n_segments = (int64_t)plan->n_segments;
+        P.lane_stride = plan->lane_stride;
+        P.avg_len = n_haystacks > 0 ? total_bytes / (uint64_t)n_haystacks : 0;
+        n_units = 2 * plan->n_segments;
+    }
+    if (kernel == 4) {
+        rc = ACB_DISPATCH(launch_global, im, B, P, out, seg_info, d, st);
+        if (rc) return rc;
+        CUDA_OK(cudaGetLastError());
+        if (ev1) {
+            CUDA_OK(cudaEventRecord(ev1, st));
+            g_timing_events.emplace_back(ev0, ev1);
+        }
+    } else if (segments) {
         DevHot hot;
         if ((rc = make_hot_view(a, dev_hot, *hot_desc, hot))) return rc;
         // the byte-indexed table is used when it exists and every row the profile saw fits on chip
@@ -747,15 +781,6 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         // the shared-memory pipe, not by instruction issue: measured equal to the compact table (162 vs 160 us).
         // Opt-in (tuning.table = 2), one segment per lane only (two per lane leave too little room for the rows).
         const bool ascii = g_tuning.table == 2 && fit128 > 0 && per_lane == 1;
-        // the grid is anchored at the 64-byte aligned address at or before the buffer; the stream
-        // bounds (offsets[0], offsets[n]) live on the device and are read by the kernels
-        P.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 63u);
-        P.seg_bytes = plan->segment_bytes;
-        P.warm = plan->warm_bytes;
-        P.n_segments = (int64_t)plan->n_segments;
-        P.lane_stride = plan->lane_stride;
-        P.avg_len = n_haystacks > 0 ? total_bytes / (uint64_t)n_haystacks : 0;
-        n_units = 2 * plan->n_segments;
         rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st, ascii, per_lane);
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());

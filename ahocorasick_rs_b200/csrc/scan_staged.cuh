@@ -313,9 +313,9 @@ __device__ __forceinline__ void advance_piece(PieceCtx &c, LaneSeg &L, const Bat
 // (hot state, nothing pending, inside a piece) or the segment is finished.
 template <int MODE, bool CP>
 __device__ __forceinline__ void settle(PieceCtx &c, LaneSeg &L, const DevImage &im, const Batch &B, const Sink &out,
-                                    SegInfo *seg_info, HotMap hm, uint32_t min_at) {
+                                    SegInfo *seg_info, HotMap hm, uint32_t min_at, bool stop_hot = true) {
     for (;;) {
-        exact_scan<MODE, CP>(c, im, out, true, min_at, hm);
+        exact_scan<MODE, CP>(c, im, out, stop_hot, min_at, hm);
         if (c.at >= c.stop && (MODE != kModeLeftmost || !c.have)) {
             advance_piece<MODE, CP>(c, L, B, out, seg_info);
             if (L.done) return;

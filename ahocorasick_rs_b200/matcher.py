@@ -103,6 +103,7 @@ class _Automaton:
 
     # ---- the hot image (rows kept in shared memory), chosen from a sample of the data ----
     HOT_TABLE_BYTES = 40 * 1024   # with 32 warps of staging buffers next to it, this is what fits on chip
+    HOT_COVERAGE_MIN = 0.99       # share of sampled state visits the hot rows must cover for the shared-memory kernel to be used
 
     def _max_hot_rows(self):
         return max(2, min(4096, self.HOT_TABLE_BYTES // (2 * self.num_columns) - 1))
@@ -141,17 +142,29 @@ class _Automaton:
                 raise RuntimeError(_capi.last_error())
             vh = visits.cpu().numpy().view(np.uint32)
             t, rows = self._upload_hot(idx, vh)
+            # How much of the sampled scan the hot rows cover.  Every byte outside them costs the staged kernel a
+            # detour through the exact scanner while 31 lanes wait; below ~99 % the segment kernel that reads the
+            # table from global memory / L2 is faster (dense automata on random text: BASELINE configs 4 and 5).
+            total_visits = int(vh.sum(dtype=np.uint64))
+            if total_visits > 0 and rows.rows < self.num_states:
+                top = np.partition(vh, len(vh) - rows.rows)[len(vh) - rows.rows:]
+                coverage = float(top.sum(dtype=np.uint64)) / total_visits
+            else:
+                coverage = 1.0
+            rows.reserved = 1 if coverage < self.HOT_COVERAGE_MIN else 0
             backoff = (st["backoff"] * 2) if st else 1
-            st = {"tensor": t, "rows": rows, "reprofile": False, "calls": 0, "backoff": backoff}
+            st = {"tensor": t, "rows": rows, "reprofile": False, "calls": 0, "backoff": backoff, "coverage": coverage}
             self._hot[idx] = st
         elif st is None:
             t, rows = self._upload_hot(idx, None)
-            st = {"tensor": t, "rows": rows, "reprofile": True, "calls": 0, "backoff": 1}
+            st = {"tensor": t, "rows": rows, "reprofile": True, "calls": 0, "backoff": 1, "coverage": 1.0}
             self._hot[idx] = st
         return st
 
     def _note_trap_stats(self, st, groups: int, traps: int):
         st["calls"] += 1
+        if st["rows"].reserved & 1:
+            return  # scanning from global memory: the hot rows are not in use
         if groups > 4096 and traps * 10 > groups and st["calls"] >= st["backoff"]:
             st["reprofile"] = True
             st["calls"] = 0
@@ -253,7 +266,8 @@ class _Automaton:
                 self._note_trap_stats(hot, tot[2], tot[3])
                 self.last_stats = {"groups": tot[2], "traps": tot[3], "repairs": tot[5], "segments": plan.n_segments,
                                    "hot_rows": hot["rows"].rows, "hot_rows128": hot["rows"].rows128,
-                                   "hot_visited": hot["rows"].visited,
+                                   "hot_visited": hot["rows"].visited, "hot_coverage": round(hot.get("coverage", 1.0), 5),
+                                   "global_table": bool(hot["rows"].reserved & 1),
                                    "segment_bytes": plan.segment_bytes, "lane_stride": plan.lane_stride}
                 if complete or (total == 0 and raw_total == 0):
                     return ws["out"][:total], ws["match_offsets"][: n + 1], total

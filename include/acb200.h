@@ -117,7 +117,9 @@ typedef struct acb_hot_desc {
     uint32_t rows;     /* rows of the compact table (column-indexed) */
     uint32_t rows128;  /* rows of the byte-indexed 128-wide table (0: patterns use bytes >= 0x7f) */
     uint32_t visited;  /* rows the profile actually saw; the rest is filler */
-    uint32_t reserved;
+    uint32_t reserved; /* flags set by the caller: bit 0 = the hot rows do not cover this data (dense automaton on
+                          adversarial input): with tuning.kernel = 0 the scan then runs from the image in global
+                          memory / L2 (kernel 4) instead of the shared-memory table */
 } acb_hot_desc;
 int acb_hot_describe(const void *host_hot, acb_hot_desc *desc);
 
@@ -203,7 +205,8 @@ int acb_timing_read(double *total_ms, uint64_t *n_scans);
 
 /* Tuning knobs (0 = library default). Affects speed only, never results. */
 typedef struct acb_tuning {
-    int kernel;        /* 0 auto, 1 = plain (one thread per haystack, table in global/L2), 2 = staged segments */
+    int kernel;        /* 0 auto, 1 = plain (one thread per haystack, table in global/L2), 2 = staged segments (hot rows in
+                          shared memory), 3 = staged, two segments per lane, 4 = segments straight from global/L2 */
     int hot_rows;      /* cap on rows kept in shared memory */
     int segment_bytes; /* segment size (rounded up to a multiple of 64 and to 8 x the warm-up) */
     int table;         /* 0 auto, 1 = column-indexed compact table only, 2 = byte-indexed 128-wide table when available */

@@ -1,0 +1,29 @@
+"""Device-resident throughput on the shapes of BASELINE configs 3, 4 and 5 (scaled to fit a quick run).
+Not part of bench.py's contract: a sanity check that the path does not fall off a cliff off config 2."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from ahocorasick_rs_b200 import AhoCorasick, BytesAhoCorasick, MatchKind, Implementation, workloads as W, _capi
+import ctypes as C
+
+def run(name, ac, data, offs, overlapping=False, steps=10):
+    d = torch.from_numpy(data).cuda(); o = torch.from_numpy(offs).cuda()
+    m, mo, total = ac.scan_device(d, o, overlapping)
+    cap = int(total * 1.2) + 1024
+    for _ in range(3): ac.scan_device(d, o, overlapping, capacity=cap, sync=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps): ac.scan_device(d, o, overlapping, capacity=cap, sync=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    st = ac._ac.last_stats if hasattr(ac, "_ac") else {}
+    print(f"{name}: {len(data)/1e6:.0f} MB, {total} matches, {ms:.3f} ms/step, {len(data)/ms/1e6:.1f} GB/s, stats {st}", flush=True)
+
+pats, data, offs = W.config3(n_patterns=10_000, n_lines=400_000)
+run("config3 (10k tokens, LeftmostLongest, 400k x 256 B)", BytesAhoCorasick(pats, MatchKind.LeftmostLongest), data, offs)
+pats, data, offs = W.config5(n_patterns=50_000, n_haystacks=25_000, hay_bytes=4096)
+run("config5 (50k patterns a-z, 25k x 4 KiB)", BytesAhoCorasick(pats), data, offs)
+pats, data = W.config4(n_patterns=100_000, hay_bytes=100_000_000)
+run("config4 (100k patterns, one 100 MB haystack, overlapping)", BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA), data,
+    np.array([0, len(data)], dtype=np.int64), overlapping=True, steps=5)

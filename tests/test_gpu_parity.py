@@ -29,7 +29,7 @@ def set_kernel(kernel=0, hot_rows=0, segment_bytes=0, table=0):
 
 
 @pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments", "staged-compact-table",
-                        "staged-byte-table", "staged-byte-table-tiny", "staged-two-per-lane", "staged-two-per-lane-tiny"])
+                        "staged-byte-table", "staged-byte-table-tiny", "staged-two-per-lane", "staged-two-per-lane-tiny", "global-segments", "global-small-segments"])
 def kernel(request):
     if request.param == "plain":
         set_kernel(1)
@@ -43,6 +43,10 @@ def kernel(request):
         set_kernel(2, 0, 0, 2)        # byte-indexed table (IDP4A transitions) wherever the patterns are ASCII
     elif request.param == "staged-byte-table-tiny":
         set_kernel(2, 7, 256, 2)      # byte-indexed table forced, 7 rows, 256-byte segments
+    elif request.param == "global-segments":
+        set_kernel(4)                 # segment-parallel, tables in global memory / L2 (what dense automata get)
+    elif request.param == "global-small-segments":
+        set_kernel(4, 0, 128)         # ... with 128-byte segments: speculation and repair everywhere
     elif request.param == "staged-two-per-lane":
         set_kernel(3)                 # two segments per lane (two interleaved chains)
     elif request.param == "staged-two-per-lane-tiny":
