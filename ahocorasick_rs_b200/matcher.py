@@ -242,8 +242,10 @@ class _Automaton:
         self.check_overlapping(overlapping)
         dev = data.device
         n = offsets.numel() - 1
-        if data.numel() >= (1 << 32) - 256:
-            raise ValueError("buffers of 4 GiB and more are not supported yet (32-bit match offsets)")
+        if data.numel() > self.WINDOW_BYTES:
+            if not sync:
+                raise ValueError(f"buffers above {self.WINDOW_BYTES} bytes are scanned in windows: sync=False is not available")
+            return self._scan_device_windows(data, offsets, overlapping, codepoints)
         img = self.image(dev)
         cap = capacity or max(1024, n * 2)
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -273,6 +275,92 @@ class _Automaton:
                     return ws["out"][:total], ws["match_offsets"][: n + 1], total
                 cap = max(total, raw_total) + max(total, raw_total) // 8 + 16
 
+    # One kernel call addresses its buffer with 32-bit offsets.  Larger inputs are cut up here: a batch into
+    # runs of whole haystacks, a single haystack above the limit into overlapping windows.
+    WINDOW_BYTES = (1 << 31)
+
+    def _scan_device_windows(self, data, offsets, overlapping, codepoints):
+        """scan_device for buffers above WINDOW_BYTES.  Same results, as int64 tensors
+        (offsets no longer fit 32 bits): (matches (k, 4) int64, match_offsets (n + 1) int64, total)."""
+        torch = _require_cuda()
+        dev = data.device
+        offs = offsets.cpu().numpy().astype(np.int64)
+        n = len(offs) - 1
+        limit = self.WINDOW_BYTES
+        parts = []          # (k, 4) int64 tensors in haystack order
+        counts = np.zeros(n, dtype=np.int64)
+        h = 0
+        while h < n:
+            if offs[h + 1] - offs[h] > limit:
+                part = self._scan_one_large(data[offs[h]:offs[h + 1]], overlapping, codepoints)
+                part[:, 0] = h
+                counts[h] = part.shape[0]
+                parts.append(part)
+                h += 1
+                continue
+            # the longest run of whole haystacks that fits one call
+            h1 = int(np.searchsorted(offs, offs[h] + limit, side="right")) - 1
+            h1 = max(h + 1, min(h1, n))
+            sub_offs = torch.from_numpy(offs[h:h1 + 1] - offs[h]).to(dev)
+            m, mo, total = self.scan_device(data[offs[h]:offs[h1]], sub_offs, overlapping, codepoints)
+            part = m.to(torch.int64) & 0xFFFFFFFF
+            part[:, 0] += h
+            counts[h:h1] = np.diff(mo.cpu().numpy().astype(np.int64))
+            parts.append(part)
+            h = h1
+        out = torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
+        mo = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum(counts, out=mo[1:])
+        return out, torch.from_numpy(mo).to(dev), int(out.shape[0])
+
+    def _scan_one_large(self, hay, overlapping, codepoints):
+        """One haystack above WINDOW_BYTES (BASELINE config 4: one 4 GiB haystack, overlapping).  Overlapping
+        searches only: windows that share max_pattern_len - 1 bytes are independent (the automaton state depends
+        on no more than that), each keeps the matches that END beyond the shared bytes.  A non-overlapping
+        search restarts at every match end, which chains the windows to each other; that case is refused."""
+        torch = _require_cuda()
+        if not overlapping:
+            raise ValueError(f"a single haystack above {self.WINDOW_BYTES} bytes is only supported with overlapping=True "
+                             "(a non-overlapping search cannot be cut into independent windows)")
+        dev = hay.device
+        total_len = hay.numel()
+        halo = max(self.max_pattern_len - 1, 0)
+        step = self.WINDOW_BYTES - halo
+        parts = []
+        cont_before = 0  # continuation bytes before the window start (code point indexes)
+        w0 = 0
+        while w0 < total_len:
+            w1 = min(w0 + self.WINDOW_BYTES, total_len)
+            window = hay[w0:w1]
+            one = torch.tensor([0, w1 - w0], dtype=torch.int64, device=dev)
+            m, _, _ = self.scan_device(window, one, True, codepoints)
+            part = m.to(torch.int64) & 0xFFFFFFFF
+            if w0 > 0 and part.shape[0]:
+                # matches ending inside the shared bytes were reported, whole, by the previous window
+                if codepoints:
+                    # the same cut in code points: ends are character boundaries, so "byte end > halo" is "code point
+                    # end > code points that start before byte `halo`" -- minus one when a character straddles that
+                    # byte (its end is beyond the shared bytes although no new character starts in between)
+                    shared_cp = halo - int(((window[:halo] & 0xC0) == 0x80).sum().item())
+                    if halo < window.numel() and (int(window[halo].item()) & 0xC0) == 0x80:
+                        shared_cp -= 1
+                    part = part[part[:, 3] > shared_cp]
+                else:
+                    part = part[part[:, 3] > halo]
+            base = (w0 - cont_before) if codepoints else w0
+            part[:, 2] += base
+            part[:, 3] += base
+            parts.append(part)
+            if w1 == total_len:
+                break
+            if codepoints:
+                nxt = w0 + step
+                for a in range(w0, nxt, 1 << 28):  # count in slices: the mask is a temporary of the slice's size
+                    b = min(a + (1 << 28), nxt)
+                    cont_before += int(((hay[a:b] & 0xC0) == 0x80).sum().item())
+            w0 += step
+        return torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
+
     def scan_host_batch(self, chunks: Sequence[bytes], overlapping: bool, codepoints: bool):
         """Host buffers in, host numpy out: (matches uint32 (k,4), match_offsets int64 (n+1))."""
         torch = _require_cuda()
@@ -293,7 +381,8 @@ class _Automaton:
         d_data = host.to(dev, non_blocking=True)[:total_bytes]
         d_offs = torch.from_numpy(offs).to(dev, non_blocking=True)
         m, moffs, _ = self.scan_device(d_data, d_offs, overlapping, codepoints)
-        return m.cpu().numpy().view(np.uint32), moffs.cpu().numpy()
+        m = m.cpu().numpy()
+        return (m.view(np.uint32) if m.dtype == np.int32 else m), moffs.cpu().numpy()
 
 
 def _as_buffer_bytes(obj) -> bytes:

@@ -27,3 +27,20 @@ run("config5 (50k patterns a-z, 25k x 4 KiB)", BytesAhoCorasick(pats), data, off
 pats, data = W.config4(n_patterns=100_000, hay_bytes=100_000_000)
 run("config4 (100k patterns, one 100 MB haystack, overlapping)", BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA), data,
     np.array([0, len(data)], dtype=np.int64), overlapping=True, steps=5)
+
+if "--large" in sys.argv:
+    # one haystack above the 2 GiB window (BASELINE config 4's shape at 2.3 GB): two windows, checked against the oracle
+    from oracle import Oracle
+    pats, data = W.config4(n_patterns=100_000, hay_bytes=2_300_000_000)
+    t0 = time.time()
+    ac = BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA)
+    d = torch.from_numpy(data).cuda()
+    o = torch.tensor([0, len(data)], dtype=torch.int64).cuda()
+    m, mo, total = ac.scan_device(d, o, overlapping=True)
+    torch.cuda.synchronize()
+    print(f"2.3 GB single haystack, overlapping: {total} matches, dtype {m.dtype}, {time.time() - t0:.1f} s incl. build/profile", flush=True)
+    tot, counts, rec = Oracle(pats, "Standard").scan_batch(data, np.array([0, len(data)], dtype=np.int64), overlapping=True)
+    got = m.cpu().numpy()
+    assert tot == total, (tot, total)
+    assert np.array_equal(got, rec.astype(np.int64)), "windowed result differs from the oracle"
+    print("matches the oracle exactly", flush=True)

@@ -247,3 +247,42 @@ def test_full_size_properties_config2():
     for h, pid, s, e in m[:200]:
         text = data[offs[h]:offs[h + 1]].tobytes().decode("utf-8")
         assert text[s:e] == pats[pid]
+
+
+# ---------------------------------------------------------------- inputs above one call's 32-bit range (cut up on the host)
+def test_windows_and_runs_match_one_call(monkeypatch):
+    """The windowing used for buffers above 2 GiB, exercised at a small limit: a batch is cut into runs of whole
+    haystacks, a single large haystack (overlapping search) into windows sharing max_pattern_len - 1 bytes."""
+    from ahocorasick_rs_b200 import matcher
+    rng = np.random.default_rng(31)
+    pats = sorted({bytes(rng.integers(97, 101, size=rng.integers(2, 9)).astype(np.uint8)) for _ in range(200)})
+    # (a) a ragged batch, all kinds
+    data, offs = W.ragged(400, 3000, b"abcd", seed=32)
+    for kind in KINDS:
+        ac = BytesAhoCorasick(pats, kind)
+        m0, o0, t0 = ac.scan_device(dev(data), dev(offs))
+        m0, o0 = m0.clone(), o0.clone()  # (views of the automaton's workspace: the next call reuses it)
+        monkeypatch.setattr(matcher._Automaton, "WINDOW_BYTES", 50_000)
+        m1, o1, t1 = ac.scan_device(dev(data), dev(offs))
+        monkeypatch.undo()
+        assert t1 == t0 and m1.dtype == torch.int64
+        assert np.array_equal(m1.cpu().numpy(), m0.cpu().numpy().view(np.uint32).astype(np.int64))
+        assert np.array_equal(o1.cpu().numpy(), o0.cpu().numpy().astype(np.int64))
+    # (b) one large haystack, overlapping, bytes and code points (multi-byte characters straddling window cuts)
+    hay = rng.integers(97, 101, size=400_000, dtype=np.uint8).astype(np.uint8)
+    exp = Oracle(pats, "Standard").find(hay.tobytes(), overlapping=True)
+    ac = BytesAhoCorasick(pats)
+    monkeypatch.setattr(matcher._Automaton, "WINDOW_BYTES", 30_001)
+    got = ac.find_matches_as_indexes(hay.tobytes(), overlapping=True)
+    with pytest.raises(ValueError):
+        ac.find_matches_as_indexes(hay.tobytes())          # non-overlapping: refused for a single oversized haystack
+    monkeypatch.undo()
+    assert got == exp
+    text = "".join(rng.choice(list("ab—é☃cd"), size=60_000))
+    upats = ["a—", "—é", "☃c", "b", "é☃c", "dd"]
+    ref = AhoCorasick(upats).find_matches_as_indexes(text, overlapping=True)
+    monkeypatch.setattr(matcher._Automaton, "WINDOW_BYTES", 9_973)
+    got = AhoCorasick(upats).find_matches_as_indexes(text, overlapping=True)
+    monkeypatch.undo()
+    assert got == ref and len(ref) > 10_000
+    assert ref == [(p, s, e) for (p, s, e) in Oracle([u.encode() for u in upats], "Standard").find_str(text, overlapping=True)]
