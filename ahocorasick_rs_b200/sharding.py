@@ -69,9 +69,14 @@ class MatchListGather:
     (cap + 1, 4) int32 block -- row 0 = (count, hay_base, complete flag, 0),
     then its first `cap` matches -- in ONE all_gather per call; the buffers are
     allocated once.  decode_gathered() turns the result into the ordered global
-    list (that is where the host finally looks at the counts)."""
+    list (that is where the host finally looks at the counts).
 
-    def __init__(self, cap: int, device, group=None):
+    overlap=True runs the exchange on a side stream: the caller's stream only
+    waits until the matches are copied out of the scan's output buffer (a few
+    microseconds), so the collective's latency overlaps the next scan.  Call
+    finish() before reading the result or timing the stream."""
+
+    def __init__(self, cap: int, device, group=None, overlap: bool = False):
         import torch
         import torch.distributed as dist
 
@@ -80,11 +85,9 @@ class MatchListGather:
         self.world = dist.get_world_size(group)
         self.block = torch.zeros((cap + 1, 4), dtype=torch.int32, device=device)
         self.everything = torch.empty(self.world * (cap + 1) * 4, dtype=torch.int32, device=device)
+        self.side = torch.cuda.Stream(device=device) if overlap and device.type == "cuda" else None
 
-    def __call__(self, matches, status, hay_base: int):
-        """matches: the (capacity, 4) int32 output buffer of scan_device(sync=False); status: its
-        8-entry int64 device status tensor ([0] = valid rows, [1] = complete flag).
-        Returns the (world, cap + 1, 4) device tensor (reused by the next call)."""
+    def _exchange(self, matches, status, hay_base: int):
         import torch.distributed as dist
 
         k = min(self.cap, matches.shape[0])
@@ -94,8 +97,34 @@ class MatchListGather:
         head[0:1].copy_(lo[0:1])
         head[2:3].copy_(lo[2:3])
         head[1:2].fill_(hay_base)
-        dist.all_gather_into_tensor(self.everything, self.block.view(-1), group=self.group)
+
+    def __call__(self, matches, status, hay_base: int):
+        """matches: the (capacity, 4) int32 output buffer of scan_device(sync=False); status: its
+        8-entry int64 device status tensor ([0] = valid rows, [1] = complete flag).
+        Returns the (world, cap + 1, 4) device tensor (reused by the next call)."""
+        import torch
+        import torch.distributed as dist
+
+        if self.side is None:
+            self._exchange(matches, status, hay_base)
+            dist.all_gather_into_tensor(self.everything, self.block.view(-1), group=self.group)
+        else:
+            main = torch.cuda.current_stream(matches.device)
+            self.side.wait_stream(main)  # the scan that produced `matches`
+            with torch.cuda.stream(self.side):
+                self._exchange(matches, status, hay_base)
+                copied = torch.cuda.Event()
+                copied.record(self.side)
+                dist.all_gather_into_tensor(self.everything, self.block.view(-1), group=self.group)
+            main.wait_event(copied)      # from here on the scan's buffers may be reused
         return self.everything.view(self.world, self.cap + 1, 4)
+
+    def finish(self):
+        """Make the caller's stream wait for the exchange in flight (overlap=True)."""
+        import torch
+
+        if self.side is not None:
+            torch.cuda.current_stream(self.block.device).wait_stream(self.side)
 
 
 def gather_match_lists_async(matches, status, hay_base: int, cap: int, group=None):

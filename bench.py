@@ -224,7 +224,7 @@ def main():
     totals = [int(ac.scan_device(*d_batches[b], capacity=cap)[2]) for b in range(2)]
     scan_stats = dict(ac._ac.last_stats)
     gather_cap = max(4096, -(-2 * max(totals) // 4096) * 4096)  # rows per rank in the match-list gather (multi-GPU)
-    gather = MatchListGather(gather_cap, dev) if world > 1 else None
+    gather = MatchListGather(gather_cap, dev, overlap=True) if world > 1 else None
     if world > 1:
         for i in range(max(args.warmup, 3)):  # warm the exchange too (communicator set-up, buffers)
             o_, _, t_ = step(i)
@@ -245,6 +245,8 @@ def main():
             # the only exchange of the path: gather the per-shard match lists (sparse, a few KB)
             # (fixed-size blocks, no host round trip: the scans of the next steps are enqueued meanwhile)
             gathered = gather(out, tot, (rank * 2 + (i & 1)) * n_hay)
+    if world > 1:
+        gather.finish()  # the exchanges ran on a side stream: the timed region ends when the last one has
     ev1.record()
     host_enqueue_ms = (time.perf_counter() - host_t0) * 1e3 / max(args.steps, 1)
     if world > 1 and args.steps > 0:
@@ -320,7 +322,7 @@ def main():
         "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "haystacks_per_gpu": n_hay, "haystack_bytes": HAY_BYTES,
                    "l2": "inputs (409.6 MB per batch, two batches alternating) are larger than L2; no flush needed",
-                   "multi_gpu": "one process per GPU, batch sharded by haystack index, table replicated; per step one gather of the match lists (NCCL)"},
+                   "multi_gpu": "one process per GPU, batch sharded by haystack index, table replicated; per step one all-gather of the match lists (NCCL, fixed-size blocks, on a side stream so that it overlaps the next scan)"},
         "matches_per_s": matches_per_step * args.steps * world / (ms_max * 1e-3),
         "matches_per_step_per_gpu": matches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
