@@ -524,13 +524,20 @@ scan_staged_kernel(DevImage im, DevHot hot_img, Batch B, SegPlan P, Sink out, Se
         }
         const uint32_t kmax = __reduce_max_sync(0xffffffffu, nch_max);
         __syncwarp();
+        // one segment per lane: the four rows this lane copies keep their (first unit, chunk count) in registers for
+        // the whole task (two per lane: there are eight and the registers are needed elsewhere; they are re-read)
+        uint2 mrow[4];
+        if (V == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) mrow[i] = lds64(cp_meta + i * 64);
+        }
 
         // stage chunk k of every row into buffer (k & 1)
         auto issue = [&](uint32_t k) {
             const uint32_t dst = cp_dst + (k & 1u) * kBufBytes;
 #pragma unroll
             for (int i = 0; i < 4 * V; i++) {
-                const uint2 m = lds64(cp_meta + i * 64);
+                const uint2 m = V == 1 ? mrow[i & 3] : lds64(cp_meta + i * 64);
                 const uint8_t *src = reinterpret_cast<const uint8_t *>(gbase) + ((size_t)(m.x + k * 4 + (lane & 3)) << 4);
                 cp_async16(dst + i * 8 * kRow, src, k < m.y ? 16u : 0u);
             }
