@@ -11,23 +11,27 @@
 //        everything to itself.  Brought in with one TMA bulk copy
 //        (cp.async.bulk + mbarrier) when the whole hot image fits; the CTA then
 //        adds the table's own shared-memory address to every entry, so an entry
-//        IS the 32-bit shared address of the next row: one three-input add
-//        (row + column + column) forms the next load address, with nothing else
-//        on the dependent chain.  A lane that left the hot set stays trapped and
+//        IS the 32-bit shared address of the next row: one multiply-add
+//        (row + 2 * column, an IMAD on the otherwise idle FMA pipe; an IDP.4A
+//        straight from the data word for the byte-indexed table) forms the next
+//        load address, with nothing else on the dependent chain.  A lane that left the hot set stays trapped and
 //        ONE compare per 64 bytes detects it; only the group something happened
 //        in is redone, through the exact scanner.  (Addresses must fit 16 bits:
 //        the table lives in the first 64 KB of shared memory.)
 //   [ column map : 256 B ]  (kColClass only)
-//   [ mbarrier ]
-//   [ copy metadata : per warp 32 x (first 16-byte unit, number of chunks) ]
-//   [ staging : per warp, 2 buffers x 32 lanes x 64 B ]  lane l's 64-byte
+//   [ mbarrier, stream bounds ]
+//   [ hot2full : (H + 1) x u32 ]  hot row -> automaton state, for the segment
+//        summaries and the hand-over to the exact scanner
+//   [ copy metadata : per warp 32 V x (first 16-byte unit, number of chunks) ]
+//   [ staging : per warp, 2 buffers x 32 V rows x 64 B ]  lane l's 64-byte
 //        chunk is row l, with its four 16-byte units XOR-swizzled by
 //        (l >> 1) & 3: the per-lane LDS.128 reads of a quarter warp hit 8
 //        different bank groups (conflict free), and a warp-wide cp.async
 //        instruction (8 rows) fills four whole 128-byte lines of shared
 //        memory.  (An 80-byte pitch without a swizzle reads just as well, but
 //        every copy instruction then straddles 12-14 lines: ncu showed 14
-//        shared-memory wavefronts per LDGSTS instead of 4.)
+//        shared-memory wavefronts per LDGSTS instead of 8, the floor.)
+//   V = segments per lane (template parameter): 1, or 2 whose chains interleave.
 //
 // All shared-memory traffic of the scan loop goes through explicit 32-bit
 // shared addresses (inline PTX): the swizzle is an XOR on the address, and the
