@@ -221,10 +221,20 @@ __device__ __forceinline__ void order_body(const OrderArgs &A) {
     }
 }
 
+// The head of dev_scratch: counters the kernels accumulate into.  Zero when a workspace is first used (the caller
+// allocates it zeroed) and zero again after every scan (the epilogue's last phase resets them).
+constexpr int kAccQueue = 0;    // u32 task counter of the staged kernel | u32 "some speculated segment start was wrong"
+constexpr int kAccRaw = 2;      // raw matches emitted (also the allocation cursor of the raw buffer)
+constexpr int kAccGroups = 3;   // 16-byte groups in the stream
+constexpr int kAccTraps = 4;    // times a lane left the hot table
+constexpr int kAccRepairs = 5;  // segment boundaries repaired
+constexpr int kAccWords = 8;
+
 // per-haystack CSR offsets into the ordered output (binary search per haystack) + the totals
 __device__ __forceinline__ void
 match_offsets_body(const acb_match *out, const unsigned long long *unit_offsets, uint64_t n_units, unsigned long long *totals,
-                   unsigned long long raw_cap, unsigned long long out_cap, int64_t n_haystacks, unsigned long long *match_offsets) {
+                   unsigned long long *acc, unsigned long long raw_cap, unsigned long long out_cap, int64_t n_haystacks,
+                   unsigned long long *match_offsets) {
     const unsigned long long total = unit_offsets[n_units];
     const unsigned long long avail = total < out_cap ? total : out_cap;
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
@@ -238,8 +248,18 @@ match_offsets_body(const acb_match *out, const unsigned long long *unit_offsets,
         }
         match_offsets[h] = (h == n_haystacks) ? total : lo;
         if (h == 0) {
+            // publish the totals, and leave the workspace's counters at zero for the next scan (nothing else
+            // touches them in this phase): a scan needs no clearing launch in front of it
+            const unsigned long long raw_total = acc[kAccRaw];
             totals[0] = total;
-            totals[1] = (totals[4] <= raw_cap && total <= out_cap) ? 1 : 0;  // complete?
+            totals[1] = (raw_total <= raw_cap && total <= out_cap) ? 1 : 0;  // complete?
+            totals[2] = acc[kAccGroups];
+            totals[3] = acc[kAccTraps];
+            totals[4] = raw_total;
+            totals[5] = acc[kAccRepairs];
+            totals[6] = totals[7] = 0;
+            acc[kAccRaw] = acc[kAccGroups] = acc[kAccTraps] = acc[kAccRepairs] = 0;
+            acc[kAccQueue] = 0;  // the scan kernel's task queue (low word) and the repair flag (high word)
         }
     }
 }
@@ -255,7 +275,7 @@ struct EpilogueArgs {
     SegPlan P;
     Sink out;
     SegInfo *seg_info;
-    unsigned long long *totals;
+    unsigned long long *totals, *acc;
     const uint32_t *unit_counts;
     uint64_t n_units;
     unsigned long long *tile_sums, *unit_offsets;
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) 
     grid.sync();
     if (E.do_repair && *reinterpret_cast<volatile unsigned int *>(E.need_repair)) {
         // rare: some guess was wrong.  Redo those places exactly, then count again.
-        repair_body<MODE, CP>(E.im, E.B, E.P, E.out, E.seg_info, E.totals + 5);
+        repair_body<MODE, CP>(E.im, E.B, E.P, E.out, E.seg_info, E.acc + kAccRepairs);
         grid.sync();
         sums();
         grid.sync();
@@ -323,17 +343,14 @@ __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) 
     // phase 3: ordered output; phase 4: per-haystack offsets into it
     order_body(E.order);
     grid.sync();
-    match_offsets_body(E.order.out, E.unit_offsets, n_items, E.totals, E.order.raw_cap, E.order.out_cap, E.B.n_haystacks,
+    match_offsets_body(E.order.out, E.unit_offsets, n_items, E.totals, E.acc, E.order.raw_cap, E.order.out_cap, E.B.n_haystacks,
                        E.match_offsets);
 }
 
-__global__ void clear_totals_kernel(unsigned long long *totals, unsigned int *task_counter) {
-    if (threadIdx.x < 8) totals[threadIdx.x] = 0;
-    if (threadIdx.x < 2) task_counter[threadIdx.x] = 0;  // [0] the scan kernel's task queue, [1] the epilogue's "repair needed" flag
-}
-
 // when the input is empty: nothing ran, publish zeros
-__global__ void zero_outputs_kernel(unsigned long long *unit_offsets, unsigned long long *match_offsets, int64_t n_haystacks) {
+__global__ void zero_outputs_kernel(unsigned long long *unit_offsets, unsigned long long *match_offsets, int64_t n_haystacks,
+                                    unsigned long long *totals) {
+    if (blockIdx.x == 0 && threadIdx.x < 8) totals[threadIdx.x] = threadIdx.x == 1 ? 1 : 0;  // no matches, complete
     for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= n_haystacks; h += (int64_t)gridDim.x * blockDim.x) match_offsets[h] = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) unit_offsets[0] = 0;
 }
@@ -488,8 +505,8 @@ int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_
     plan->n_units = seg_units > n_haystacks ? seg_units : n_haystacks;
     if (plan->n_units < 1) plan->n_units = 1;
     const uint64_t tiles = (plan->n_units + kScanTile - 1) / kScanTile;
-    // [0] task counter, repair flag | unit tile sums | cont tile sums | cont_cum (n_segments + 1) | packed cont tails (u32)
-    plan->scratch_words = 2 + (tiles + 1) + (tiles + 1) + (plan->n_segments + 2) + (plan->n_segments / 2 + 2);
+    // [0..7] counters (kAcc* in capi.cu) | unit tile sums | cont tile sums | cont_cum (n_segments + 1) | packed cont tails (u32)
+    plan->scratch_words = 8 + (tiles + 1) + (tiles + 1) + (plan->n_segments + 2) + (plan->n_segments / 2 + 2);
     return ACB_OK;
 }
 
@@ -716,15 +733,14 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     out.raw_aux = ws->dev_raw_aux;
     out.cap = ws->raw_capacity;
     out.unit_counts = ws->dev_unit_counts;
-    out.raw_total = totals + 4;
+    unsigned long long *acc = reinterpret_cast<unsigned long long *>(ws->dev_scratch);  // zero between scans (see kAcc*)
+    out.raw_total = acc + kAccRaw;
     SegInfo *seg_info = reinterpret_cast<SegInfo *>(ws->dev_seg_info);
 
-    clear_totals_kernel<<<1, 32, 0, st>>>(totals, task_counter);
-    g_launches++;
     unsigned long long *unit_offsets = reinterpret_cast<unsigned long long *>(ws->dev_unit_offsets);
     unsigned long long *match_offsets = reinterpret_cast<unsigned long long *>(ws->dev_match_offsets);
     if (n_haystacks == 0 || total_bytes == 0) {
-        zero_outputs_kernel<<<(unsigned)((n_haystacks + 256) / 256), 256, 0, st>>>(unit_offsets, match_offsets, n_haystacks);
+        zero_outputs_kernel<<<(unsigned)((n_haystacks + 256) / 256), 256, 0, st>>>(unit_offsets, match_offsets, n_haystacks, totals);
         g_launches++;
         CUDA_OK(cudaGetLastError());
         return ACB_OK;
@@ -781,7 +797,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         // the shared-memory pipe, not by instruction issue: measured equal to the compact table (162 vs 160 us).
         // Opt-in (tuning.table = 2), one segment per lane only (two per lane leave too little room for the rows).
         const bool ascii = g_tuning.table == 2 && fit128 > 0 && per_lane == 1;
-        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, totals + 2, st, ascii, per_lane);
+        rc = ACB_DISPATCH(launch_staged_cols, h, im, hot, B, P, out, seg_info, d, task_counter, acc + kAccGroups, st, ascii, per_lane);
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());
         if (ev1) {
@@ -799,7 +815,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     }
     // repair -> counts -> offsets -> ordered output -> per-haystack offsets: one cooperative kernel
     const uint64_t max_tiles = (plan->n_units + kScanTile - 1) / kScanTile;
-    unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + 2;
+    unsigned long long *tile_sums = reinterpret_cast<unsigned long long *>(ws->dev_scratch) + kAccWords;
     unsigned long long *cont_tiles = tile_sums + max_tiles + 1;
     unsigned long long *cont_cum = cont_tiles + max_tiles + 1;
     uint32_t *cont_dense = reinterpret_cast<uint32_t *>(cont_cum + plan->n_segments + 2);
@@ -809,7 +825,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     A.raw_unit = ws->dev_raw_unit;
     A.raw_aux = ws->dev_raw_aux;
     A.raw_cap = ws->raw_capacity;
-    A.raw_total = totals + 4;
+    A.raw_total = acc + kAccRaw;
     A.unit_offsets = unit_offsets;
     A.unit_counts = ws->dev_unit_counts;
     A.seg_info = segments ? seg_info : nullptr;
@@ -828,6 +844,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     E.out = out;
     E.seg_info = seg_info;
     E.totals = totals;
+    E.acc = acc;
     E.unit_counts = ws->dev_unit_counts;
     E.n_units = n_units;
     E.tile_sums = tile_sums;

@@ -198,7 +198,7 @@ class _Automaton:
                 "unit_counts": torch.empty(n_units, dtype=torch.int32, device=dev),
                 "unit_offsets": torch.empty(n_units + 1, dtype=torch.int64, device=dev),
                 "seg_info": torch.empty((n_seg, 8), dtype=torch.int32, device=dev),
-                "scratch": torch.empty(n_scr, dtype=torch.int64, device=dev),
+                "scratch": torch.zeros(n_scr, dtype=torch.int64, device=dev),  # zeroed: its head holds the kernels' counters
                 "total": torch.zeros(8, dtype=torch.int64, device=dev),
                 "out": torch.empty((cap, 4), dtype=torch.int32, device=dev),
                 "match_offsets": torch.empty(n_hay + 1, dtype=torch.int64, device=dev),

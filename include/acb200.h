@@ -157,7 +157,9 @@ typedef struct acb_workspace {
     uint32_t *dev_unit_counts;   /* [plan.n_units] */
     uint64_t *dev_unit_offsets;  /* [plan.n_units + 1] */
     void *dev_seg_info;          /* [plan.n_segments * 32 bytes] per-segment summaries */
-    uint64_t *dev_scratch;       /* [plan.scratch_words] */
+    uint64_t *dev_scratch;       /* [plan.scratch_words]; its first 8 words must be ZERO the first time a workspace is
+                                    used: they hold the kernels' counters, and every completed scan leaves them zeroed
+                                    again (so a scan needs no clearing launch in front of it) */
     uint64_t *dev_total;         /* [8]: [0] = matches found, [1] = 1 when dev_out holds all of them (0: buffers too
                                     small, retry), [2] = 16-byte groups in the stream, [3] = times a lane left the hot table
                                     for the exact scanner, [4] = raw matches emitted, [5] = segment boundaries repaired */
