@@ -163,3 +163,66 @@ def scan_sharded(scan_fn: Callable, data: np.ndarray, offsets: np.ndarray, group
     sub_data = data[offsets[lo]: offsets[hi]]
     local = scan_fn(sub_data, sub_offs.astype(np.int64))
     return gather_match_lists(local, lo, group=group)
+
+
+def scan_sharded_single(scan_fn: Callable, data: np.ndarray, max_pattern_len: int, group=None, codepoints: bool = False):
+    """ONE large haystack, overlapping search, across the ranks.  Rank r owns
+    the bytes [a_r, b_r) of a contiguous split and scans [a_r - halo, b_r) with
+    halo = max_pattern_len - 1: the automaton state depends on no more than that, so the
+    windows are independent; each rank keeps the matches that END in (a_r, b_r] (every match
+    has exactly one such owner) and the lists are gathered in rank order, which is the
+    reference's order (by end, then start, then pattern).
+
+    scan_fn(window uint8 array) -> (k, 3) or (k, 4) integer tensor/array whose last three
+    columns are (pattern, start, end) relative to the window -- byte offsets, or code point
+    indexes when codepoints=True (the ranks then exchange how many continuation bytes each
+    of them owns, to rebase the indexes).  Returns the global (k, 4) int64 tensor
+    (0, pattern, start, end) on every rank.  Non-overlapping searches do not shard this way
+    (restarts chain the ranges); the caller must not use this for them."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n = len(data)
+    a, b = (n * rank) // world, (n * (rank + 1)) // world
+    halo = max(max_pattern_len - 1, 0)
+    w0 = max(a - halo, 0)
+    window = data[w0:b]
+    got = scan_fn(window)
+    got = got.cpu() if hasattr(got, "cpu") else torch.from_numpy(np.ascontiguousarray(got))
+    got = got.to(torch.int64).reshape(got.shape[0], -1)
+    local = torch.zeros((got.shape[0], 4), dtype=torch.int64)
+    local[:, 1:] = got[:, -3:]
+    shared = a - w0  # bytes of the window that belong to the previous ranks
+    base = w0
+    if codepoints:
+        is_cont = (window & 0xC0) == 0x80
+        # keep "byte end > shared" expressed in code points (see matcher._scan_one_large for the straddling case)
+        shared_cp = shared - int(is_cont[:shared].sum())
+        if shared < len(window) and is_cont[shared]:
+            shared_cp -= 1
+        keep = local[:, 3] > shared_cp if rank > 0 else torch.ones(local.shape[0], dtype=torch.bool)
+        owned = torch.tensor([int(is_cont[shared:].sum())], dtype=torch.int64)  # continuation bytes in [a, b)
+        counts = torch.zeros(world, dtype=torch.int64)
+        dist.all_gather_into_tensor(counts, owned, group=group)
+        cont_before_a = int(counts[:rank].sum())
+        cont_before_w0 = cont_before_a - int(is_cont[:shared].sum())
+        base = w0 - cont_before_w0
+    else:
+        keep = local[:, 3] > shared if rank > 0 else torch.ones(local.shape[0], dtype=torch.bool)
+    local = local[keep]
+    local[:, 2] += base
+    local[:, 3] += base
+    # gather with 64-bit records (offsets of a multi-gigabyte haystack): counts first, then padded blocks
+    cnt = torch.tensor([local.shape[0]], dtype=torch.int64)
+    cnts = torch.zeros(world, dtype=torch.int64)
+    dist.all_gather_into_tensor(cnts, cnt, group=group)
+    kmax = max(int(cnts.max()), 1)
+    padded = torch.zeros((kmax, 4), dtype=torch.int64)
+    padded[: local.shape[0]] = local
+    everything = torch.zeros(world * kmax * 4, dtype=torch.int64)
+    dist.all_gather_into_tensor(everything, padded.view(-1), group=group)
+    everything = everything.view(world, kmax, 4)
+    return torch.cat([everything[r, : int(cnts[r])] for r in range(world)], dim=0)
+

@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 from ahocorasick_rs_b200 import workloads as W
 from ahocorasick_rs_b200.sharding import (decode_gathered, gather_match_lists, gather_match_lists_async, partition_by_bytes,
-                                          scan_sharded)
+                                          scan_sharded, scan_sharded_single)
 
 
 def test_partition_by_bytes_covers_everything():
@@ -75,6 +75,27 @@ def _worker(rank, world, port, q):
         ok = False
     except RuntimeError:
         pass
+    # one large haystack, overlapping, split across the ranks with a halo (bytes, then code points)
+    rng = np.random.default_rng(9)
+    hay = rng.integers(97, 100, size=50_001, dtype=np.uint8).astype(np.uint8)
+    exp1 = orc.find(hay.tobytes(), overlapping=True)
+    got1 = scan_sharded_single(lambda w: np.array(orc.find(w.tobytes(), overlapping=True), dtype=np.int64).reshape(-1, 3),
+                               hay, max_pattern_len=3)
+    ok = ok and [tuple(int(x) for x in r[1:]) for r in got1.tolist()] == exp1
+    text = "".join(rng.choice(list("ab—é☃c"), size=20_000))
+    upats = ["a—", "—é", "☃c", "b", "é☃c"]
+    uorc = Oracle([u.encode() for u in upats], "Standard")
+    exp2 = uorc.find_str(text, overlapping=True)
+    raw = np.frombuffer(text.encode(), dtype=np.uint8)
+
+    def scan_cp(w):
+        # window-relative code point indexes: the oracle's own byte -> code point map over the window's bytes
+        wb = w.tobytes()
+        cont = np.cumsum(np.concatenate([[0], (np.frombuffer(wb, dtype=np.uint8) & 0xC0) == 0x80]))
+        return np.array([(p, s - cont[s], e - cont[e]) for (p, s, e) in uorc.find(wb, overlapping=True)], dtype=np.int64).reshape(-1, 3)
+
+    got2 = scan_sharded_single(scan_cp, raw, max_pattern_len=max(len(u.encode()) for u in upats), codepoints=True)
+    ok = ok and [tuple(int(x) for x in r[1:]) for r in got2.tolist()] == exp2 and len(exp2) > 1000
     q.put((rank, bool(ok), int(full.shape[0])))
     dist.destroy_process_group()
 
