@@ -4,8 +4,6 @@
 #include <stdexcept>
 #include <string>
 #include <utility>
-#include <cmath>
-#include <cstdlib>
 #include <vector>
 
 #include <cooperative_groups.h>
@@ -71,7 +69,7 @@ profile_kernel(DevImage im, Batch B, uint32_t *visits, int64_t n_samples, uint32
 }
 
 // ---------------------------------------------------------------------------
-// exclusive prefix sum u32[n] (strided) -> u64[n+1] (three small kernels)
+// exclusive prefix sum u32[n] (strided) -> u64[n+1]: building blocks of the epilogue kernel's phases 1 and 2
 // ---------------------------------------------------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanItems = 8;
@@ -267,7 +265,7 @@ match_offsets_body(const acb_match *out, const unsigned long long *unit_offsets,
 // ---------------------------------------------------------------------------
 // everything after the scan in ONE cooperative kernel (grid-wide barriers
 // between the phases): repair -> prefix sums -> ordered output -> per-haystack
-// offsets.  Ten tiny launches cost more than the work they do.
+// offsets.  (As ten separate launches this cost more than the work they do.)
 // ---------------------------------------------------------------------------
 struct EpilogueArgs {
     DevImage im;
