@@ -50,6 +50,54 @@ def _require_cuda():
     return torch
 
 
+def _count_cont(x) -> int:
+    """UTF-8 continuation bytes (10xxxxxx) in a uint8 numpy array or torch tensor."""
+    return int(((x & 0xC0) == 0x80).sum())
+
+
+def scan_in_windows(scan_window, hay, window_bytes: int, halo: int, codepoints: bool):
+    """An OVERLAPPING search over one haystack too large for one call, as independent windows that share `halo` =
+    max_pattern_len - 1 bytes (the automaton state depends on no more than that).  scan_window(window) returns the
+    window's matches as rows (haystack, pattern, start, end), window-relative, byte offsets or code point indexes.
+    Every window keeps the matches that END beyond the bytes it shares with its predecessor (those were reported,
+    whole, by the predecessor), rebased to the haystack.  `hay` is a uint8 numpy array or torch tensor; returns the
+    list of per-window row blocks, in order (concatenated they are in the reference's order)."""
+    total_len = len(hay)
+    step = window_bytes - halo
+    if step <= 0:
+        raise ValueError("window smaller than the longest pattern")
+    parts = []
+    cont_before = 0  # continuation bytes before the window start (code point indexes)
+    w0 = 0
+    while w0 < total_len:
+        w1 = min(w0 + window_bytes, total_len)
+        window = hay[w0:w1]
+        part = scan_window(window)
+        if w0 > 0 and part.shape[0]:
+            if codepoints:
+                # the same cut in code points: ends are character boundaries, so "byte end > halo" is "code point
+                # end > code points that start before byte `halo`" -- minus one when a character straddles that
+                # byte (its end is beyond the shared bytes although no new character starts in between)
+                shared_cp = halo - _count_cont(window[:halo])
+                if halo < len(window) and (int(window[halo]) & 0xC0) == 0x80:
+                    shared_cp -= 1
+                part = part[part[:, 3] > shared_cp]
+            else:
+                part = part[part[:, 3] > halo]
+        base = (w0 - cont_before) if codepoints else w0
+        part[:, 2] += base
+        part[:, 3] += base
+        parts.append(part)
+        if w1 == total_len:
+            break
+        if codepoints:
+            nxt = w0 + step
+            for a in range(w0, nxt, 1 << 28):  # count in slices: the mask is a temporary of the slice's size
+                cont_before += _count_cont(hay[a:min(a + (1 << 28), nxt)])
+        w0 += step
+    return parts
+
+
 class _Automaton:
     """Owns the host automaton handle, its device image and a growable device
     workspace.  Shared by both public classes."""
@@ -323,42 +371,13 @@ class _Automaton:
             raise ValueError(f"a single haystack above {self.WINDOW_BYTES} bytes is only supported with overlapping=True "
                              "(a non-overlapping search cannot be cut into independent windows)")
         dev = hay.device
-        total_len = hay.numel()
-        halo = max(self.max_pattern_len - 1, 0)
-        step = self.WINDOW_BYTES - halo
-        parts = []
-        cont_before = 0  # continuation bytes before the window start (code point indexes)
-        w0 = 0
-        while w0 < total_len:
-            w1 = min(w0 + self.WINDOW_BYTES, total_len)
-            window = hay[w0:w1]
-            one = torch.tensor([0, w1 - w0], dtype=torch.int64, device=dev)
+
+        def scan_window(window):
+            one = torch.tensor([0, window.numel()], dtype=torch.int64, device=dev)
             m, _, _ = self.scan_device(window, one, True, codepoints)
-            part = m.to(torch.int64) & 0xFFFFFFFF
-            if w0 > 0 and part.shape[0]:
-                # matches ending inside the shared bytes were reported, whole, by the previous window
-                if codepoints:
-                    # the same cut in code points: ends are character boundaries, so "byte end > halo" is "code point
-                    # end > code points that start before byte `halo`" -- minus one when a character straddles that
-                    # byte (its end is beyond the shared bytes although no new character starts in between)
-                    shared_cp = halo - int(((window[:halo] & 0xC0) == 0x80).sum().item())
-                    if halo < window.numel() and (int(window[halo].item()) & 0xC0) == 0x80:
-                        shared_cp -= 1
-                    part = part[part[:, 3] > shared_cp]
-                else:
-                    part = part[part[:, 3] > halo]
-            base = (w0 - cont_before) if codepoints else w0
-            part[:, 2] += base
-            part[:, 3] += base
-            parts.append(part)
-            if w1 == total_len:
-                break
-            if codepoints:
-                nxt = w0 + step
-                for a in range(w0, nxt, 1 << 28):  # count in slices: the mask is a temporary of the slice's size
-                    b = min(a + (1 << 28), nxt)
-                    cont_before += int(((hay[a:b] & 0xC0) == 0x80).sum().item())
-            w0 += step
+            return m.to(torch.int64) & 0xFFFFFFFF
+
+        parts = scan_in_windows(scan_window, hay, self.WINDOW_BYTES, max(self.max_pattern_len - 1, 0), codepoints)
         return torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
 
     def scan_host_batch(self, chunks: Sequence[bytes], overlapping: bool, codepoints: bool):

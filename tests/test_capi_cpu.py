@@ -121,3 +121,36 @@ def test_many_patterns_construction():
     pats = [f"p{i}_{i * 7919 % 1000}_" for i in range(30_000)]
     ac = AhoCorasick(pats)
     assert ac._ac.n_patterns == 30_000 and ac._patterns is None
+
+
+def test_scan_in_windows_against_the_oracle():
+    """The window cut used for haystacks above one call's range (matcher.scan_in_windows), with the oracle as the
+    per-window scanner: byte offsets and code point indexes, multi-byte characters straddling the cuts."""
+    import numpy as np
+    from ahocorasick_rs_b200.matcher import scan_in_windows
+    from oracle import Oracle
+
+    rng = np.random.default_rng(17)
+    text = "".join(rng.choice(list("ab—é☃cd"), size=30_000))
+    upats = ["a—", "—é", "☃c", "b", "é☃c", "dd", "—"]
+    orc = Oracle([u.encode() for u in upats], "Standard")
+    raw = np.frombuffer(text.encode(), dtype=np.uint8)
+    halo = max(len(u.encode()) for u in upats) - 1
+
+    def bytes_scan(w):
+        return np.array([(0, p, s, e) for (p, s, e) in orc.find(w.tobytes(), overlapping=True)], dtype=np.int64).reshape(-1, 4)
+
+    def cp_scan(w):
+        wb = w.tobytes()
+        cont = np.cumsum(np.concatenate([[0], (np.frombuffer(wb, dtype=np.uint8) & 0xC0) == 0x80]))
+        return np.array([(0, p, s - cont[s], e - cont[e]) for (p, s, e) in orc.find(wb, overlapping=True)], dtype=np.int64).reshape(-1, 4)
+
+    exp_b = orc.find(raw.tobytes(), overlapping=True)
+    exp_c = orc.find_str(text, overlapping=True)
+    assert len(exp_b) > 5000
+    for wbytes in (halo + 1, 17, 1000, 4099, len(raw) + 5):
+        got = np.concatenate(scan_in_windows(bytes_scan, raw, wbytes, halo, False))
+        assert [tuple(r[1:]) for r in got.tolist()] == exp_b, wbytes
+        got = np.concatenate(scan_in_windows(cp_scan, raw, wbytes, halo, True))
+        assert [tuple(r[1:]) for r in got.tolist()] == exp_c, wbytes
+
