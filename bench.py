@@ -194,6 +194,10 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at the VERSION debug
+        # level) out of it; anything more verbose that the caller asked for is left alone
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     L = _capi.lib()
