@@ -286,3 +286,43 @@ def test_windows_and_runs_match_one_call(monkeypatch):
     monkeypatch.undo()
     assert got == ref and len(ref) > 10_000
     assert ref == [(p, s, e) for (p, s, e) in Oracle([u.encode() for u in upats], "Standard").find_str(text, overlapping=True)]
+
+
+# ---------------------------------------------------------------- the reference's property tests, through the drop-in classes
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.text(), st.text(min_size=1), st.text(), st.sampled_from([True, False, None]))
+def test_unicode_extensive_like_the_reference(prefix, pattern, suffix, store_patterns):
+    """reference tests/test_ac.py:135-154: one arbitrary unicode pattern inside arbitrary text; every hit slices back
+    to the pattern, and the first hit is where str.find puts it."""
+    haystack = prefix + pattern + suffix
+    ac = AhoCorasick([pattern]) if store_patterns is None else AhoCorasick([pattern], store_patterns=store_patterns)
+    idx = ac.find_matches_as_indexes(haystack)
+    assert {i for (i, _, _) in idx} == {0}
+    assert {haystack[s:e] for (_, s, e) in idx} == {pattern}
+    assert set(ac.find_matches_as_strings(haystack)) == {pattern}
+    assert idx[0][1] == haystack.find(pattern)
+
+
+@settings(max_examples=25, deadline=None)
+@given(st.lists(st.text(min_size=3), min_size=1, max_size=300), st.sampled_from([True, False, None]))
+def test_construction_extensive_like_the_reference(patterns, store_patterns):
+    """reference tests/test_ac.py:86-100 (pattern lists scaled down from 30 000 to 300 per example: every
+    call here is a GPU round trip; the 30 000-pattern construction itself is in the CPU tests)."""
+    patterns = [f"{p}_{i}_" for (i, p) in enumerate(patterns)]
+    ac = AhoCorasick(patterns, store_patterns=store_patterns)
+    for p in patterns[:40]:
+        assert ac.find_matches_as_strings(p) == [p]
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.binary(), st.binary(min_size=1), st.binary())
+def test_bytes_extensive_like_the_reference(prefix, pattern, suffix):
+    """reference tests/test_ac_bytes.py:133-161: arbitrary bytes, including 0x00 and 0xff."""
+    haystack = prefix + pattern + suffix
+    idx = BytesAhoCorasick([pattern]).find_matches_as_indexes(haystack)
+    assert {i for (i, _, _) in idx} == {0}
+    assert {haystack[s:e] for (_, s, e) in idx} == {pattern}
+    assert idx[0][1] == haystack.find(pattern)
