@@ -8,6 +8,17 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# Property tests draw the SAME examples on every run and on every box (and keep no example database): a green
+# suite here is a green suite at the round-end run, not a new random sample.
+try:
+    from hypothesis import settings as _hyp_settings
+
+    _hyp_settings.register_profile("repo", derandomize=True, deadline=None, database=None)
+    _hyp_settings.load_profile("repo")
+except ImportError:  # hypothesis is optional for the non-property tests
+    pass
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
