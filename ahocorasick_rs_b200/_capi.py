@@ -17,7 +17,7 @@ ACB_EINVAL, ACB_EBUILD, ACB_EUNSUPPORTED, ACB_ECUDA, ACB_ECAPACITY = -1, -2, -3,
 class Plan(C.Structure):
     _fields_ = [("n_segments", C.c_uint64), ("n_units", C.c_uint64), ("scratch_words", C.c_uint64),
                 ("segment_bytes", C.c_uint32), ("warm_bytes", C.c_uint32), ("lane_stride", C.c_uint32),
-                ("reserved", C.c_uint32)]
+                ("task_bytes", C.c_uint32)]
 
 
 class Workspace(C.Structure):
@@ -32,6 +32,11 @@ class Workspace(C.Structure):
 
 class Tuning(C.Structure):
     _fields_ = [("kernel", C.c_int), ("hot_rows", C.c_int), ("segment_bytes", C.c_int), ("table", C.c_int)]
+
+
+class SieveDesc(C.Structure):
+    _fields_ = [("window", C.c_uint32), ("last_level", C.c_uint32), ("probes", C.c_uint32), ("bloom_bytes", C.c_uint32),
+                ("nodes", C.c_uint32), ("keys", C.c_uint32), ("filter_entries", C.c_uint32), ("table_slots", C.c_uint32)]
 
 
 class HotDesc(C.Structure):
@@ -76,10 +81,30 @@ def lib():
         L.acb_hot_rows.restype = C.c_uint32
         L.acb_hot_rows.argtypes = [C.c_void_p]
         L.acb_hot_describe.argtypes = [C.c_void_p, C.POINTER(HotDesc)]
-        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HotDesc), C.c_void_p, C.c_void_p, C.c_int64,
+        L.acb_sieve_build.restype = C.c_uint64
+        L.acb_sieve_build.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.acb_sieve_write.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.acb_sieve_describe.argtypes = [C.c_void_p, C.POINTER(SieveDesc)]
+        L.acb_scan_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(HotDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_uint64, C.c_int, C.c_int, C.POINTER(Plan), C.POINTER(Workspace), C.c_void_p]
         _lib = L
     return _lib
+
+
+_tls = __import__("threading").local()
+
+
+def set_tuning(kernel: int = 0, hot_rows: int = 0, segment_bytes: int = 0, table: int = 0) -> None:
+    """acb_set_tuning for the calling thread (the library keeps the knobs per thread); the host layer reads
+    the choice back with current_kernel() to decide which device images a scan needs."""
+    t = Tuning(kernel, hot_rows, segment_bytes, table)
+    if lib().acb_set_tuning(C.byref(t)) != ACB_OK:
+        raise RuntimeError(last_error())
+    _tls.kernel = kernel
+
+
+def current_kernel() -> int:
+    return getattr(_tls, "kernel", 0)
 
 
 def last_error() -> str:
@@ -92,4 +117,5 @@ EXPORTS = [
     "acb_image_write", "acb_plan_scan", "acb_scan_batch",
     "acb_launch_count", "acb_set_tuning", "acb_timing_enable", "acb_timing_read",
     "acb_profile", "acb_hot_bytes", "acb_hot_build", "acb_hot_rows", "acb_hot_describe",
+    "acb_sieve_build", "acb_sieve_write", "acb_sieve_describe",
 ]

@@ -234,6 +234,8 @@ Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_
         throw std::runtime_error("transition table would need " + std::to_string(trans_bytes >> 20) + " MiB");
     auto *A = new Automaton();
     A->implementation = implementation;
+    A->pat_offs.assign(offsets, offsets + n + 1);
+    if (n && offsets[n]) A->pat_blob.assign(blob, blob + offsets[n]);
     ImageHeader &h = A->hdr;
     h.magic = kImageMagic;
     h.version = 1;

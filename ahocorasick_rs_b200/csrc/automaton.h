@@ -5,6 +5,7 @@
 // out for HBM rather than for a CPU cache: see DESIGN.md "Data layout".
 #pragma once
 #include <cstdint>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -76,6 +77,12 @@ struct Automaton {
     ImageHeader hdr{};
     std::vector<uint8_t> image;  // header + tables, ready to copy to the device
     int implementation = -1;
+    // the patterns themselves (the sieve image is built from them on demand: sieve.h)
+    std::vector<uint8_t> pat_blob;
+    std::vector<uint64_t> pat_offs;
+    std::mutex sieve_mutex;
+    std::vector<uint8_t> sieve;       // built by acb_sieve_build
+    uint32_t sieve_bloom_max = 0, sieve_w_max = 0;
 };
 
 // Builds the automaton; throws std::runtime_error with a message on failure.

@@ -1,4 +1,5 @@
 // capi.cu -- the C ABI (include/acb200.h): planning, kernel dispatch, ordering passes.
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
@@ -11,6 +12,7 @@
 #include "repair.cuh"
 #include "scan_staged.cuh"
 #include "scan_global.cuh"
+#include "scan_sieve.cuh"
 
 namespace acb {
 
@@ -345,6 +347,192 @@ __global__ void __launch_bounds__(kScanThreads) epilogue_kernel(EpilogueArgs E) 
                        E.match_offsets);
 }
 
+
+// ---------------------------------------------------------------------------
+// Epilogue of the sieve scan (scan_sieve.cuh).  The scan leaves the OVERLAPPING
+// match list as raw records tagged (task, rank in task); tasks are in stream
+// order, so the ordered list needs prefix sums and one placement pass, no sort.
+// Non-overlapping searches then SELECT from that list, per haystack (SURVEY.md
+// 8c: "among occurrences with start >= s pick the minimum of (end, start, pid) /
+// (start, pid) / (start, -end, pid)"; the list is sorted by (end, start, pid)),
+// and the selected records are packed.  One cooperative launch.
+// ---------------------------------------------------------------------------
+struct SieveEpiArgs {
+    Batch B;
+    uint32_t *unit_counts;               // [n_tasks] from the scan; later [n_haystacks] selected per haystack
+    uint64_t n_tasks;
+    unsigned long long *tile_sums, *unit_offsets;  // unit_offsets: [n_tasks + 1]; later [n_haystacks] first record of each haystack
+    const uint32_t *cont_tail;           // [n_tasks] (code points)
+    unsigned long long *cont_tiles, *cont_cum;
+    const acb_match *raw;
+    const uint32_t *raw_seq, *raw_unit, *raw_aux;
+    unsigned long long raw_cap;
+    acb_match *ordered;                  // the overlapping list, ordered (overlapping search: the output buffer)
+    acb_match *final_out;                // non-overlapping: the output buffer
+    unsigned long long out_cap;
+    const uint32_t *pat_cplen;
+    int64_t origin;
+    uint32_t task_bytes;
+    uint32_t max_pat_len;
+    int longest;                         // kModeLeftmost: 1 = LeftmostLongest, 0 = LeftmostFirst
+    unsigned long long *totals, *acc, *match_offsets;
+};
+
+// index of the first record of `list[0 .. n)` whose haystack is >= h
+__device__ __forceinline__ unsigned long long first_of_haystack(const acb_match *list, unsigned long long n, int64_t h) {
+    unsigned long long lo = 0, hi = n;
+    while (lo < hi) {
+        const unsigned long long mid = (lo + hi) >> 1;
+        if ((int64_t)list[mid].haystack < h)
+            lo = mid + 1;
+        else
+            hi = mid;
+    }
+    return lo;
+}
+
+// The reference's non-overlapping iteration over ONE haystack, as a selection from its overlapping list r[0 .. n)
+// (sorted by end, start, pattern).  The selected records are packed to the front; returns how many.
+template <int MODE>
+__device__ __forceinline__ uint32_t select_non_overlapping(acb_match *r, unsigned long long n, uint32_t max_len, int longest) {
+    unsigned long long w = 0;
+    uint32_t s = 0;  // the search restarts here (the end of the previous match)
+    if (MODE == kModeStandard) {
+        // the first occurrence, in list order, that starts at or after s
+        for (unsigned long long i = 0; i < n; i++) {
+            const uint4 m = reinterpret_cast<const uint4 *>(r)[i];
+            if (m.z >= s) {
+                reinterpret_cast<uint4 *>(r)[w++] = m;
+                s = m.w;
+            }
+        }
+        return (uint32_t)w;
+    }
+    unsigned long long i = 0;
+    while (i < n) {
+        bool have = false;
+        uint4 best = make_uint4(0, 0, 0, 0);
+        for (unsigned long long j = i; j < n; j++) {
+            const uint4 m = reinterpret_cast<const uint4 *>(r)[j];
+            if (have && m.w > best.z + max_len) break;  // everything from here on starts after `best` does
+            if (m.z < s) continue;
+            bool better = !have || m.z < best.z;
+            if (have && m.z == best.z) better = longest ? (m.w > best.w || (m.w == best.w && m.y < best.y)) : (m.y < best.y);
+            if (better) {
+                best = m;
+                have = true;
+            }
+        }
+        if (!have) break;
+        reinterpret_cast<uint4 *>(r)[w++] = best;  // w <= i: only records that can no longer be chosen are overwritten
+        s = best.w;
+        while (i < n && r[i].end <= s) i++;
+    }
+    return (uint32_t)w;
+}
+
+template <int MODE, bool CP>
+__global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiArgs E) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const uint64_t tiles = (E.n_tasks + kScanTile - 1) / kScanTile;
+    const uint64_t ctiles = CP ? tiles : 0;
+    // phase 1 + 2: where each task's matches go (and, code points, the continuation bytes before each task)
+    for (uint64_t tt = blockIdx.x; tt < tiles + ctiles; tt += gridDim.x) {
+        if (tt >= tiles)
+            tile_sum_body<false>(E.cont_tail, 1, E.n_tasks, E.cont_tiles, tt - tiles, nullptr);
+        else
+            tile_sum_body<false>(E.unit_counts, 1, E.n_tasks, E.tile_sums, tt, nullptr);
+    }
+    grid.sync();
+    for (uint64_t tt = blockIdx.x; tt < tiles + ctiles; tt += gridDim.x) {
+        if (tt >= tiles)
+            tile_apply_body<false>(E.cont_tail, 1, E.n_tasks, E.cont_tiles, E.cont_cum, tt - tiles);
+        else
+            tile_apply_body<false>(E.unit_counts, 1, E.n_tasks, E.tile_sums, E.unit_offsets, tt);
+    }
+    grid.sync();
+    // phase 3: the ordered overlapping list
+    {
+        unsigned long long n = E.acc[kAccRaw];
+        if (n > E.raw_cap) n = E.raw_cap;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+             i += (unsigned long long)gridDim.x * blockDim.x) {
+            const uint32_t u = E.raw_unit[i];
+            const unsigned long long dst = E.unit_offsets[u] + E.raw_seq[i];
+            if (dst >= E.out_cap) continue;
+            uint4 r = reinterpret_cast<const uint4 *>(E.raw)[i];  // haystack, pattern, start, end (bytes)
+            if (CP) {
+                unsigned long long cont = E.raw_aux[i];
+                const int64_t hs = E.B.offsets[r.x];
+                const int64_t t_lo = E.origin + (int64_t)u * (int64_t)E.task_bytes;
+                if (hs < t_lo) {
+                    // the haystack began in an earlier task: add what the tasks in between counted
+                    const int64_t u0 = (hs - E.origin) / (int64_t)E.task_bytes;
+                    cont += E.cont_cum[u] - E.cont_cum[u0];
+                }
+                const uint32_t end_cp = r.w - (uint32_t)cont;
+                r.w = end_cp;
+                r.z = end_cp - E.pat_cplen[r.y];
+            }
+            reinterpret_cast<uint4 *>(E.ordered)[dst] = r;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) E.totals[6] = E.unit_offsets[E.n_tasks];
+    }
+    grid.sync();
+    const unsigned long long list_total = E.totals[6];
+    const unsigned long long avail = list_total < E.out_cap ? list_total : E.out_cap;
+    if (MODE == kModeOverlap) {
+        for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x)
+            E.match_offsets[h] = (h == E.B.n_haystacks) ? list_total : first_of_haystack(E.ordered, avail, h);
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long raw_total = E.acc[kAccRaw];
+            E.totals[0] = list_total;
+            E.totals[1] = (raw_total <= E.raw_cap && list_total <= E.out_cap) ? 1 : 0;
+            E.totals[2] = E.totals[3] = E.totals[5] = 0;
+            E.totals[4] = raw_total > list_total ? raw_total : list_total;
+            E.totals[7] = 0;
+            E.acc[kAccRaw] = E.acc[kAccGroups] = E.acc[kAccTraps] = E.acc[kAccRepairs] = 0;
+            E.acc[kAccQueue] = 0;
+        }
+        return;
+    }
+    // phase 4: per haystack, select the non-overlapping matches and pack them to the front of the haystack's stretch
+    const uint64_t n_hay = (uint64_t)E.B.n_haystacks;
+    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long lo = first_of_haystack(E.ordered, avail, h), hi = first_of_haystack(E.ordered, avail, h + 1);
+        E.unit_offsets[h] = lo;
+        E.unit_counts[h] = hi > lo ? select_non_overlapping<MODE>(E.ordered + lo, hi - lo, E.max_pat_len, E.longest) : 0u;
+    }
+    grid.sync();
+    // phase 5 + 6: per-haystack offsets into the output
+    const uint64_t htiles = (n_hay + kScanTile - 1) / kScanTile;
+    for (uint64_t tt = blockIdx.x; tt < htiles; tt += gridDim.x) tile_sum_body<false>(E.unit_counts, 1, n_hay, E.tile_sums, tt, nullptr);
+    grid.sync();
+    for (uint64_t tt = blockIdx.x; tt < htiles; tt += gridDim.x) tile_apply_body<false>(E.unit_counts, 1, n_hay, E.tile_sums, E.match_offsets, tt);
+    grid.sync();
+    // phase 7: pack
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < avail; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint4 r = reinterpret_cast<const uint4 *>(E.ordered)[i];
+        const unsigned long long k = i - E.unit_offsets[r.x];
+        if (k < E.unit_counts[r.x]) {
+            const unsigned long long dst = E.match_offsets[r.x] + k;
+            if (dst < E.out_cap) reinterpret_cast<uint4 *>(E.final_out)[dst] = r;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long raw_total = E.acc[kAccRaw];
+        const unsigned long long total = n_hay ? E.match_offsets[n_hay] : 0;
+        E.totals[0] = total;
+        E.totals[1] = (raw_total <= E.raw_cap && list_total <= E.out_cap) ? 1 : 0;
+        E.totals[2] = E.totals[3] = E.totals[5] = 0;
+        E.totals[4] = raw_total > list_total ? raw_total : list_total;  // room the overlapping list needs
+        E.totals[7] = 0;
+        E.acc[kAccRaw] = E.acc[kAccGroups] = E.acc[kAccTraps] = E.acc[kAccRepairs] = 0;
+        E.acc[kAccQueue] = 0;
+    }
+}
+
 // when the input is empty: nothing ran, publish zeros
 __global__ void zero_outputs_kernel(unsigned long long *unit_offsets, unsigned long long *match_offsets, int64_t n_haystacks,
                                     unsigned long long *totals) {
@@ -364,13 +552,15 @@ struct acb_automaton {
     Automaton *impl;
 };
 
+// Per-thread state only: the last error, the tuning knobs and the optional kernel timing belong to the calling
+// thread (two automata scanned from two threads do not see each other's settings); the launch counter is atomic.
 static thread_local std::string g_err;
-static unsigned long long g_launches = 0;
-static acb_tuning g_tuning = {0, 0, 0, 0};  // kernel, hot_rows, segment_bytes, table
+static std::atomic<unsigned long long> g_launches{0};
+static thread_local acb_tuning g_tuning = {0, 0, 0, 0};  // kernel, hot_rows, segment_bytes, table
 
 // optional device timing of the dominant (scan) kernel, for bench.py's roofline
-static bool g_timing = false;
-static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
+static thread_local bool g_timing = false;
+static thread_local std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_timing_events;
 
 static int fail(int code, const std::string &msg) {
     g_err = msg;
@@ -387,7 +577,7 @@ extern "C" {
 
 const char *acb_last_error(void) { return g_err.c_str(); }
 const char *acb_version(void) { return "acb200 0.2 (sm_100a)"; }
-uint64_t acb_launch_count(void) { return g_launches; }
+uint64_t acb_launch_count(void) { return g_launches.load(); }
 
 int acb_timing_enable(int on) {
     g_timing = on != 0;
@@ -476,6 +666,58 @@ int acb_hot_describe(const void *host_hot, acb_hot_desc *desc) {
     return ACB_OK;
 }
 
+uint64_t acb_sieve_build(acb_automaton *a, uint32_t bloom_bytes_max, uint32_t w_max) {
+    if (!a) {
+        fail(ACB_EINVAL, "null argument");
+        return 0;
+    }
+    Automaton &A = *a->impl;
+    std::lock_guard<std::mutex> lock(A.sieve_mutex);
+    if (A.sieve.empty() || A.sieve_bloom_max != bloom_bytes_max || A.sieve_w_max != w_max) {
+        try {
+            sieve_image_build(A.pat_blob.data(), A.pat_offs.data(), A.hdr.n_patterns, bloom_bytes_max, w_max, A.sieve);
+            A.sieve_bloom_max = bloom_bytes_max;
+            A.sieve_w_max = w_max;
+        } catch (const std::exception &e) {
+            A.sieve.clear();
+            fail(ACB_EBUILD, e.what());
+            return 0;
+        }
+    }
+    return A.sieve.size();
+}
+
+int acb_sieve_write(acb_automaton *a, void *host_dst, uint64_t dst_bytes) {
+    if (!a || !host_dst) return fail(ACB_EINVAL, "null argument");
+    Automaton &A = *a->impl;
+    std::lock_guard<std::mutex> lock(A.sieve_mutex);
+    if (A.sieve.empty()) return fail(ACB_EINVAL, "acb_sieve_build has not been called");
+    if (dst_bytes < A.sieve.size()) return fail(ACB_ECAPACITY, "sieve image buffer too small");
+    std::memcpy(host_dst, A.sieve.data(), A.sieve.size());
+    return ACB_OK;
+}
+
+int acb_sieve_describe(const void *host_sieve, acb_sieve_desc *d) {
+    const SieveHeader *h = static_cast<const SieveHeader *>(host_sieve);
+    if (!h || !d || h->magic != kSieveMagic) return fail(ACB_EINVAL, "not a sieve image");
+    d->window = h->W;
+    d->last_level = h->last_level;
+    d->probes = h->n_probes;
+    d->bloom_bytes = h->bloom_words * 4;
+    d->nodes = h->n_nodes;
+    d->keys = h->n_keys;
+    d->filter_entries = h->n_filter_entries;
+    d->table_slots = h->ht_mask + 1;
+    return ACB_OK;
+}
+
+// tasks of the sieve kernel: a multiple of 512 bytes (tuning.segment_bytes when the sieve kernel is forced, else 8 KiB)
+static uint32_t sieve_task_bytes() {
+    uint32_t t = (g_tuning.kernel == 5 && g_tuning.segment_bytes > 0) ? (uint32_t)g_tuning.segment_bytes : 8192u;
+    t = (t + 511u) & ~511u;
+    return t < 512u ? 512u : t;
+}
+
 int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_bytes, uint64_t n_haystacks, acb_plan *plan) {
     if (!a || !plan) return fail(ACB_EINVAL, "null argument");
     const uint32_t L = a->impl->hdr.max_pat_len;
@@ -498,13 +740,18 @@ int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_
         if (stride > 65536) stride = 65536;
     }
     plan->lane_stride = (uint32_t)stride;
-    plan->reserved = 0;
+    // the sieve kernel's tasks: a grid anchored at the 512-byte aligned address at or before the buffer
+    plan->task_bytes = sieve_task_bytes();
+    const uint64_t mis512 = reinterpret_cast<uintptr_t>(dev_bytes) & 511u;
+    const uint64_t n_tasks = (total_bytes + mis512 + plan->task_bytes - 1) / plan->task_bytes;
     const uint64_t seg_units = 2 * plan->n_segments;
     plan->n_units = seg_units > n_haystacks ? seg_units : n_haystacks;
+    if (plan->n_units < n_tasks) plan->n_units = n_tasks;
     if (plan->n_units < 1) plan->n_units = 1;
     const uint64_t tiles = (plan->n_units + kScanTile - 1) / kScanTile;
-    // [0..7] counters (kAcc* in capi.cu) | unit tile sums | cont tile sums | cont_cum (n_segments + 1) | packed cont tails (u32)
-    plan->scratch_words = 8 + (tiles + 1) + (tiles + 1) + (plan->n_segments + 2) + (plan->n_segments / 2 + 2);
+    const uint64_t per_piece = plan->n_segments > n_tasks ? plan->n_segments : n_tasks;  // segments or tasks, whichever kernel runs
+    // [0..7] counters (kAcc* in capi.cu) | unit tile sums | cont tile sums | cont_cum (pieces + 1) | packed cont tails (u32)
+    plan->scratch_words = 8 + (tiles + 1) + (tiles + 1) + (per_piece + 2) + (per_piece / 2 + 2);
     return ACB_OK;
 }
 
@@ -654,6 +901,73 @@ template <int MODE, bool CP>
 int launch_epilogue(EpilogueArgs &E, const DeviceInfo &d, cudaStream_t st) {
     auto kern = epilogue_kernel<MODE, CP>;
     static thread_local int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    static thread_local int cached_device = -1;  // the occupancy answer belongs to a device
+    if (cached_device != d.device) {
+        for (auto &row : blocks_per_sm) row[0] = row[1] = 0;
+        cached_device = d.device;
+    }
+    int &bps = blocks_per_sm[MODE][CP ? 1 : 0];
+    if (bps == 0) {
+        CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kScanThreads, 0));
+        if (bps < 1) return fail(ACB_ECUDA, "epilogue kernel does not fit on an SM");
+        if (bps > 4) bps = 4;
+    }
+    void *args[] = {&E};
+    CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * bps), dim3(kScanThreads), args, 0, st));
+    g_launches++;
+    return ACB_OK;
+}
+
+
+DevSieve make_sieve_view(const SieveHeader &h, const void *dev_sieve) {
+    const uint8_t *b = static_cast<const uint8_t *>(dev_sieve);
+    DevSieve v;
+    v.bloom = reinterpret_cast<const uint32_t *>(b + h.off_bloom);
+    v.ht = reinterpret_cast<const SieveSlot *>(b + h.off_ht);
+    v.na = reinterpret_cast<const SieveNodeA *>(b + h.off_node_a);
+    v.nb = reinterpret_cast<const SieveNodeB *>(b + h.off_node_b);
+    v.pids = reinterpret_cast<const uint32_t *>(b + h.off_pids);
+    v.W = h.W;
+    v.last_level = h.last_level;
+    v.n_probes = h.n_probes;
+    v.bloom_words = h.bloom_words;
+    v.prim_words = h.prim_words;
+    v.ht_size = h.ht_mask + 1;
+    v.max_pat_len = h.max_pat_len;
+    return v;
+}
+
+template <bool CP>
+int launch_sieve(const DevSieve &sv, const Batch &B, const SievePlan &P, const Sink &out, uint32_t *cont_tail, unsigned int *task_counter,
+                 const DeviceInfo &d, cudaStream_t st) {
+    const uint32_t smem = sv.bloom_words * 4 + kSieveSmemFixed;
+    if ((int)smem > d.max_smem_optin) return fail(ACB_ECUDA, "the sieve's filter does not fit in shared memory (rebuild it with a smaller bloom_bytes_max)");
+#define ACB_SIEVE_GO(WC)                                                                                  \
+    do {                                                                                                  \
+        auto kern = sieve_scan_kernel<CP, WC>;                                                            \
+        CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem_optin)); \
+        kern<<<d.sms, kSieveThreads, smem, st>>>(sv, B, P, out, cont_tail, task_counter);                 \
+    } while (0)
+    if (sv.W < 4)
+        ACB_SIEVE_GO(0);
+    else if (sv.W == 4)
+        ACB_SIEVE_GO(1);
+    else
+        ACB_SIEVE_GO(2);
+#undef ACB_SIEVE_GO
+    g_launches++;
+    return ACB_OK;
+}
+
+template <int MODE, bool CP>
+int launch_sieve_epilogue(SieveEpiArgs &E, const DeviceInfo &d, cudaStream_t st) {
+    auto kern = sieve_epilogue_kernel<MODE, CP>;
+    static thread_local int blocks_per_sm[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    static thread_local int cached_device = -1;
+    if (cached_device != d.device) {
+        for (auto &row : blocks_per_sm) row[0] = row[1] = 0;
+        cached_device = d.device;
+    }
     int &bps = blocks_per_sm[MODE][CP ? 1 : 0];
     if (bps == 0) {
         CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, kScanThreads, 0));
@@ -697,7 +1011,7 @@ int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *de
 }
 
 int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, const acb_hot_desc *hot_desc,
-                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
+                   const void *dev_sieve, const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
                    int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream) {
     if (!a || !dev_image || !dev_offsets || n_haystacks < 0 || !plan) return fail(ACB_EINVAL, "bad argument");
     if (n_haystacks > 0xfffffffell) return fail(ACB_EINVAL, "too many haystacks in one batch");
@@ -719,7 +1033,8 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     // the plan must be the one acb_plan_scan gives for these arguments (it sizes the workspace)
     acb_plan want;
     acb_plan_scan(a, dev_bytes, total_bytes, (uint64_t)n_haystacks, &want);
-    if (want.n_segments != plan->n_segments || want.segment_bytes != plan->segment_bytes || want.n_units != plan->n_units)
+    if (want.n_segments != plan->n_segments || want.segment_bytes != plan->segment_bytes || want.n_units != plan->n_units ||
+        want.task_bytes != plan->task_bytes)
         return fail(ACB_EINVAL, "plan does not match the arguments (call acb_plan_scan again)");
 
     unsigned long long *totals = reinterpret_cast<unsigned long long *>(ws->dev_total);
@@ -745,10 +1060,86 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     }
 
     int kernel = g_tuning.kernel;
-    if (kernel == 0) kernel = 2;
+    if (kernel == 0) kernel = dev_sieve ? 5 : 2;  // the caller uploads a sieve image when it wants the position-parallel scan
     // the caller's profile says the hot rows do not cover this data: scan from the image in global memory / L2
     if (kernel == 2 && g_tuning.kernel == 0 && hot_desc && (hot_desc->reserved & 1u)) kernel = 4;
-    if ((!dev_hot || !hot_desc) && kernel != 4) kernel = 1;  // no hot image: the plain kernel (one thread per haystack)
+    if (kernel == 5 && !dev_sieve) return fail(ACB_EINVAL, "the sieve kernel needs a sieve image (acb_sieve_build / acb_sieve_write)");
+    if ((!dev_hot || !hot_desc) && kernel != 4 && kernel != 5) kernel = 1;  // no hot image: the plain kernel (one thread per haystack)
+    if (kernel == 5) {
+        // ---- position-parallel scan: filter + exact verification, then order (+ select) ----
+        const Automaton &A = *a->impl;
+        SieveHeader sh;
+        {
+            std::lock_guard<std::mutex> lock(a->impl->sieve_mutex);
+            if (A.sieve.size() < sizeof(SieveHeader)) return fail(ACB_EINVAL, "acb_sieve_build has not been called");
+            std::memcpy(&sh, A.sieve.data(), sizeof(sh));
+        }
+        const DevSieve sv = make_sieve_view(sh, dev_sieve);
+        SievePlan SP;
+        SP.origin = -(int64_t)(reinterpret_cast<uintptr_t>(dev_bytes) & 511u);
+        SP.task_bytes = plan->task_bytes;
+        SP.n_tasks = (int64_t)((total_bytes + (uint64_t)(-SP.origin) + plan->task_bytes - 1) / plan->task_bytes);
+        SP.buf_bytes = total_bytes;
+        SP.avg_len = total_bytes / (uint64_t)n_haystacks;
+        if (SP.avg_len < 1) SP.avg_len = 1;
+        const uint64_t cap = ws->raw_capacity < ws->out_capacity ? ws->raw_capacity : ws->out_capacity;
+        // scratch: counters | unit tile sums | cont tile sums | cont_cum | cont tails (u32)
+        const uint64_t tiles_max = (plan->n_units + kScanTile - 1) / kScanTile;
+        unsigned long long *tile_sums = acc + kAccWords;
+        unsigned long long *cont_tiles = tile_sums + tiles_max + 1;
+        unsigned long long *cont_cum = cont_tiles + tiles_max + 1;
+        const uint64_t per_piece = plan->n_segments > (uint64_t)SP.n_tasks ? plan->n_segments : (uint64_t)SP.n_tasks;
+        uint32_t *cont_tail = reinterpret_cast<uint32_t *>(cont_cum + per_piece + 2);
+        // a non-overlapping search orders the list into dev_raw's place and packs its selection into dev_out, so its
+        // raw records go through dev_out first
+        out.raw = mode == kModeOverlap ? ws->dev_raw : ws->dev_out;
+        out.cap = cap;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        if (g_timing) {
+            CUDA_OK(cudaEventCreate(&e0));
+            CUDA_OK(cudaEventCreate(&e1));
+            CUDA_OK(cudaEventRecord(e0, st));
+        }
+        rc = cp ? launch_sieve<true>(sv, B, SP, out, cont_tail, task_counter, d, st)
+                : launch_sieve<false>(sv, B, SP, out, cont_tail, task_counter, d, st);
+        if (rc) return rc;
+        CUDA_OK(cudaGetLastError());
+        if (e1) {
+            CUDA_OK(cudaEventRecord(e1, st));
+            g_timing_events.emplace_back(e0, e1);
+        }
+        SieveEpiArgs E;
+        E.B = B;
+        E.unit_counts = ws->dev_unit_counts;
+        E.n_tasks = (uint64_t)SP.n_tasks;
+        E.tile_sums = tile_sums;
+        E.unit_offsets = unit_offsets;
+        E.cont_tail = cont_tail;
+        E.cont_tiles = cont_tiles;
+        E.cont_cum = cont_cum;
+        E.raw = out.raw;
+        E.raw_seq = ws->dev_raw_seq;
+        E.raw_unit = ws->dev_raw_unit;
+        E.raw_aux = ws->dev_raw_aux;
+        E.raw_cap = cap;
+        E.ordered = mode == kModeOverlap ? ws->dev_out : ws->dev_raw;
+        E.final_out = ws->dev_out;
+        E.out_cap = cap;
+        E.pat_cplen = im.pat_cplen;
+        E.origin = SP.origin;
+        E.task_bytes = SP.task_bytes;
+        E.max_pat_len = h.max_pat_len;
+        E.longest = kind == ACB_LEFTMOST_LONGEST ? 1 : 0;
+        E.totals = totals;
+        E.acc = acc;
+        E.match_offsets = match_offsets;
+        rc = mode == kModeStandard   ? (cp ? launch_sieve_epilogue<kModeStandard, true>(E, d, st) : launch_sieve_epilogue<kModeStandard, false>(E, d, st))
+             : mode == kModeLeftmost ? (cp ? launch_sieve_epilogue<kModeLeftmost, true>(E, d, st) : launch_sieve_epilogue<kModeLeftmost, false>(E, d, st))
+                                     : (cp ? launch_sieve_epilogue<kModeOverlap, true>(E, d, st) : launch_sieve_epilogue<kModeOverlap, false>(E, d, st));
+        if (rc) return rc;
+        CUDA_OK(cudaGetLastError());
+        return ACB_OK;
+    }
     const bool segments = kernel == 2 || kernel == 3 || kernel == 4;
     const int per_lane = kernel == 3 ? 2 : 1;  // segments per lane of the staged kernel (3: two interleaved chains)
     SegPlan P{};

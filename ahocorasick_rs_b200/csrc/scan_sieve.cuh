@@ -1,0 +1,478 @@
+// scan_sieve.cuh -- the position-parallel scan (see sieve.h for the idea and the image).
+//
+// One persistent CTA per SM, 32 warps.  Dynamic shared memory:
+//   [ primary bitmap | secondary Bloom filter : bloom_words x u32 ]   one TMA bulk copy (cp.async.bulk + mbarrier)
+//   [ mbarrier ]
+//   [ per warp: 16 B history | 512 B window | 16 B pad ]   the "stash": the text the warp is looking at, for the
+//        few positions that survive the first probe (their hash is recomputed from here, the on-chip walk reads
+//        older bytes from here); written only when a window has survivors
+//
+// Work: the byte stream is cut into TASKS of task_bytes (a multiple of 512) on a grid anchored at a 512-byte aligned
+// address; warps claim tasks from an atomic counter and walk them in 512-byte WINDOWS: lane l holds bytes
+// [16 l, 16 l + 16) of the window in registers (one coalesced LDG.128 per lane, two windows prefetched ahead).
+//
+// Per window:
+//   fast path   for each of its 16 bytes a lane forms the W-byte window ending there (funnel shifts over its own words and
+//               the two words before them, which come from the neighbouring lane), hashes it (one IMAD; two for W > 4)
+//               and tests ONE bit of the filter: IMAD.HI (word) + LEA + LDS + SHF (bit) + SHF (collect).  No chain,
+//               no branch: 16 independent probes per lane.
+//   stage 1     lanes with survivors (a few % of positions) redo them from the stash: remaining probes, then the
+//               on-chip walk towards the pattern start through the deeper filter levels.  What is left needs the
+//               exact check.
+//   stage 2     those positions, in stream order, 32 at a time (one per lane): hash table -> reverse-trie walk in global
+//               memory / L2 -> the deepest terminal node = every pattern ending there; matches are written with ONE
+//               atomicAdd per round (warp-aggregated reservation; ranks by shuffle prefix sums), each tagged with
+//               (task, rank in task) so that the epilogue can place it without a sort.
+//
+// Output of this kernel = the OVERLAPPING match list.  sieve_epilogue_kernel (capi.cu) orders it and, for the
+// non-overlapping searches, selects from it per haystack.
+#pragma once
+#include "scan_staged.cuh"
+#include "sieve.h"
+
+namespace acb {
+
+constexpr int kSieveWarps = 32;
+constexpr int kSieveThreads = kSieveWarps * 32;
+constexpr uint32_t kWin = 512;                       // bytes per warp window
+constexpr uint32_t kStashBytes = 16 + kWin + 16;     // per warp
+constexpr uint32_t kSieveSmemFixed = 16 + kSieveWarps * kStashBytes;  // mbarrier slot + stashes (after the filter)
+
+struct DevSieve {
+    const uint32_t *bloom;
+    const SieveSlot *ht;
+    const SieveNodeA *na;
+    const SieveNodeB *nb;
+    const uint32_t *pids;
+    uint32_t W, last_level, n_probes, bloom_words, prim_words, ht_size, max_pat_len;
+};
+
+struct SievePlan {
+    int64_t origin;      // stream position of task 0's start (<= 0; dev_bytes + origin is 512-byte aligned)
+    int64_t n_tasks;
+    uint64_t buf_bytes;  // length of the byte buffer (loads stay inside [0, buf_bytes))
+    uint64_t avg_len;    // hint for the first haystack lookup of a task
+    uint32_t task_bytes;
+};
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32v(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr));
+    return v;
+}
+// (hi:lo) >> (s & 31), low word
+__device__ __forceinline__ uint32_t shf_r_wrap(uint32_t lo, uint32_t hi, uint32_t s) {
+    uint32_t d;
+    asm("shf.r.wrap.b32 %0, %1, %2, %3;\n" : "=r"(d) : "r"(lo), "r"(hi), "r"(s));
+    return d;
+}
+
+// 16 bytes at stream position q, zero outside [vlo, vhi) (the stream, clipped to the buffer)
+__device__ __forceinline__ uint4 load_chunk(const uint8_t *bytes, int64_t q, int64_t vlo, int64_t vhi) {
+    if (q >= vlo && q + 16 <= vhi) return __ldg(reinterpret_cast<const uint4 *>(bytes + q));
+    uint32_t w[4] = {0, 0, 0, 0};
+    if (q + 16 > vlo && q < vhi) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            const int64_t p = q + k;
+            if (p >= vlo && p < vhi) w[k >> 2] |= (uint32_t)__ldg(bytes + p) << (8 * (k & 3));
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// continuation bytes among the first nbytes (0..16) of the 16-byte chunk at shared address a
+__device__ __forceinline__ uint32_t cont_prefix(uint32_t a, uint32_t nbytes) {
+    uint32_t n = 0;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t v = lds32v(a + 4 * w);
+        const int left = (int)nbytes - 4 * w;
+        const uint32_t mask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u));
+        n += __popc(v & ~(v << 1) & 0x80808080u & mask);
+    }
+    return n;
+}
+
+__device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, uint32_t *total) {
+    uint32_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (uint32_t)d) x += y;
+    }
+    *total = __shfl_sync(0xffffffffu, x, 31);
+    return x - v;
+}
+
+// WC: 0 = W < 4 (the window word is shifted down), 1 = W == 4, 2 = W in 5..8 (two words)
+template <bool CP, int WC>
+__global__ void __launch_bounds__(kSieveThreads, 1)
+sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_tail, unsigned int *task_counter) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t bloom_s = (uint32_t)__cvta_generic_to_shared(smem);
+    const uint32_t bloom_bytes = sv.bloom_words * 4;
+    const uint32_t bar_s = bloom_s + bloom_bytes;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t stash_s = bar_s + 16 + warp * kStashBytes;  // history at +0, window at +16
+    const uint32_t n_words = sv.prim_words;                       // the primary bitmap (fast path)
+    const uint32_t sec_s = bloom_s + sv.prim_words * 4;           // the secondary filter
+    const uint32_t sec_words = sv.bloom_words - sv.prim_words;
+
+    // ---- prologue: the filter ----------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        mbar_init(bar_s, 1);
+        mbar_expect_tx(bar_s, bloom_bytes);
+        tma_bulk_g2s(bloom_s, sv.bloom, bloom_bytes, bar_s);
+    }
+    // the pad behind each window stays zero (stage 1 reads one aligned word past the last byte)
+    if (lane < 4) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(stash_s + 16 + kWin + lane * 4), "r"(0u) : "memory");
+    __syncthreads();
+    mbar_wait(bar_s, 0);
+
+    const int64_t stream_lo = __ldg(B.offsets), stream_hi = __ldg(B.offsets + B.n_haystacks);
+    // bytes that may be read: the stream, inside the buffer
+    const int64_t vlo = max(stream_lo, (int64_t)0), vhi = min(stream_hi, (int64_t)P.buf_bytes);
+    const uint32_t W = sv.W;
+    const uint32_t sh_lo = 8u * (4u - min(W, 4u)), sh_hi = 8u * (8u - max(W, 4u));
+    const uint32_t T = P.task_bytes;
+
+    auto sec_bit = [&](uint32_t p) -> uint32_t {
+        const uint32_t word = lds32v(sec_s + __umulhi(p, sec_words) * 4u);
+        return (word >> (p & 31u)) & 1u;
+    };
+    auto sec_has = [&](uint32_t x) -> bool { return sec_bit(x * kMulB) && (sv.n_probes < 2 || sec_bit(x * kMulC)); };
+    // the 8 bytes ending at window-relative byte index i (inclusive), from the stash: (lo', hi') as the filter keys them
+    auto stash_key = [&](int i, uint32_t &klo, uint32_t &khi) {
+        const uint32_t a = stash_s + 16 + (uint32_t)(i - 7);  // i - 7 >= -16 + ... : history covers 16 bytes
+        const uint32_t j = a & ~3u, r = (a & 3u) * 8u;
+        const uint32_t w0 = lds32v(j), w1 = lds32v(j + 4), w2 = lds32v(j + 8);
+        const uint32_t hi = shf_r_wrap(w0, w1, r), lo = shf_r_wrap(w1, w2, r);
+        klo = W <= 4 ? lo >> sh_lo : lo;
+        khi = W <= 4 ? 0u : hi >> sh_hi;
+    };
+
+    unsigned int claimed = 0;
+    if (lane == 0) claimed = atomicAdd(task_counter, 1u);
+    for (;;) {
+        const unsigned int task = __shfl_sync(0xffffffffu, claimed, 0);
+        if ((int64_t)task >= P.n_tasks) break;
+        if (lane == 0) claimed = atomicAdd(task_counter, 1u);  // the next one: its round trip overlaps this task
+        const int64_t t_lo = P.origin + (int64_t)task * T;
+        const int64_t lo = max(t_lo, vlo), hi = min(t_lo + (int64_t)T, vhi);
+        if (lo >= hi) {
+            if (lane == 0) {
+                out.unit_counts[task] = 0;
+                if (CP) cont_tail[task] = 0;
+            }
+            continue;
+        }
+        // positions (= index of a window's LAST byte) that can end a match: the window must lie inside the stream
+        const int64_t plo = max(lo, vlo + (int64_t)W - 1);
+        int64_t wbase = t_lo + ((lo - t_lo) & ~(int64_t)(kWin - 1));
+        const int64_t wlast = t_lo + ((hi - 1 - t_lo) & ~(int64_t)(kWin - 1));
+
+        // ---- haystack bookkeeping: lane l caches offsets[hb + l] (stream positions fit 32 bits: one call scans < 4 GiB) ----
+        int64_t hb;
+        {
+            int64_t h = P.avg_len ? (int64_t)((uint64_t)(lo - stream_lo) / P.avg_len) : 0;
+            if (h >= B.n_haystacks) h = B.n_haystacks - 1;
+            if (!(__ldg(B.offsets + h) <= lo && lo < __ldg(B.offsets + h + 1))) h = find_haystack(B, lo);
+            hb = h;
+        }
+        auto load_offc = [&](int64_t base) -> uint32_t {
+            const int64_t idx = base + lane;
+            return idx <= B.n_haystacks ? (uint32_t)__ldg(B.offsets + idx) : 0xffffffffu;
+        };
+        uint32_t offc = load_offc(hb);
+        // haystack containing byte p (p >= the first cached offset) and its start.  The shuffles are executed by the whole
+        // warp; a window with more than 31 haystack starts (haystacks of a few bytes) falls back to a search per lane.
+        auto hay_of = [&](int64_t p, int64_t &hs) -> int64_t {
+            uint32_t l = 0;
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const uint32_t c = l + step;
+                const uint32_t v = __shfl_sync(0xffffffffu, offc, c & 31);
+                if (c < 32 && (int64_t)v <= p) l = c;
+            }
+            hs = (int64_t)__shfl_sync(0xffffffffu, offc, l);
+            int64_t h = hb + l;
+            if (l == 31 && h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= p) {
+                h = find_haystack(B, p);
+                hs = __ldg(B.offsets + h);
+            }
+            return h;
+        };
+
+        uint32_t n_emitted = 0;
+        // code points: continuation bytes seen by this lane in earlier windows of the task | count at the start of the
+        // haystack that holds the byte before the window (0 while that haystack began before the task)
+        uint32_t cp_lane = 0, cp_base = 0;
+        int64_t h_prev = hb;  // haystack holding the byte before the window (first window: the one holding `lo`)
+
+        uint32_t carry_z = 0, carry_w = 0;
+        {
+            const uint4 c = load_chunk(B.bytes, wbase - 16, vlo, vhi);
+            carry_z = c.z;
+            carry_w = c.w;
+            if (lane == 0) sts128(stash_s, c);
+        }
+        uint4 cur = load_chunk(B.bytes, wbase + 16 * lane, vlo, vhi);
+        uint4 nx1 = make_uint4(0, 0, 0, 0), nx2 = make_uint4(0, 0, 0, 0);
+        if (wbase + kWin <= wlast) nx1 = load_chunk(B.bytes, wbase + kWin + 16 * lane, vlo, vhi);
+
+        for (;; wbase += kWin) {
+            if (wbase + 2 * (int64_t)kWin <= wlast) nx2 = load_chunk(B.bytes, wbase + 2 * kWin + 16 * lane, vlo, vhi);
+            // ---- fast path: first filter probe for the 16 positions of this lane ----
+            uint32_t pz = __shfl_up_sync(0xffffffffu, cur.z, 1), pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
+            if (lane == 0) {
+                pz = carry_z;
+                pw = carry_w;
+            }
+            const uint32_t a[6] = {pz, pw, cur.x, cur.y, cur.z, cur.w};
+            uint32_t acc = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                const int j = 2 + (k >> 2), r = k & 3;
+                const uint32_t wlo = r == 3 ? a[j] : __funnelshift_r(a[j - 1], a[j], 8 * (r + 1));
+                uint32_t x;
+                if (WC == 2) {
+                    const uint32_t whi = r == 3 ? a[j - 1] : __funnelshift_r(a[j - 2], a[j - 1], 8 * (r + 1));
+                    x = wlo + (whi >> sh_hi) * kMixHi;
+                } else if (WC == 1) {
+                    x = wlo;
+                } else {
+                    x = wlo >> sh_lo;
+                }
+                const uint32_t p = x * kMulA;
+                const uint32_t word = lds32(bloom_s + __umulhi(p, n_words) * 4u);
+                acc = __funnelshift_r(acc, shf_r_wrap(word, 0u, p), 1);  // bit (p & 31) of the word -> top of acc
+            }
+            uint32_t m1 = acc >> 16;
+            // positions outside [plo, hi) cannot end a match (first and last window of the task only)
+            const int64_t q = wbase + 16 * lane;
+            if (wbase < plo || wbase + (int64_t)kWin > hi) {
+                const int from = (int)min(max(plo - q, (int64_t)0), (int64_t)16), to = (int)min(max(hi - q, (int64_t)0), (int64_t)16);
+                m1 &= ((1u << to) - 1u) & ~((1u << from) - 1u);
+            }
+            uint32_t wc = 0;  // code points: continuation bytes in this lane's chunk
+            if (CP) {
+                if ((cur.x | cur.y | cur.z | cur.w) & 0x80808080u) wc = cont_bytes(cur.x) + cont_bytes(cur.y) + cont_bytes(cur.z) + cont_bytes(cur.w);
+            }
+            const int64_t wend = min(wbase + (int64_t)kWin, hi);  // one past the last stream byte of this window
+            // does the cached offset range still cover this window?  (31 haystack starts ahead at most)
+            bool refreshed = false;
+            {
+                const uint32_t o1 = __shfl_sync(0xffffffffu, offc, 1);
+                if ((int64_t)o1 <= wbase) {
+                    // the window starts beyond haystack hb: move the cache forward to the haystack holding max(wbase, lo)
+                    const int64_t first = max(wbase, lo);
+                    const uint32_t ahead = __popc(__ballot_sync(0xffffffffu, (int64_t)offc <= first));
+                    if (ahead == 32) {
+                        hb = find_haystack(B, first);
+                    } else {
+                        hb += ahead - 1;
+                    }
+                    offc = load_offc(hb);
+                    refreshed = true;
+                }
+            }
+            (void)refreshed;
+            const bool any = __any_sync(0xffffffffu, m1 != 0);
+            // code points need the stash (and the prefix of wc) when a haystack starts inside the window, too
+            const uint32_t o1 = __shfl_sync(0xffffffffu, offc, 1);
+            const bool boundary_inside = CP && (int64_t)o1 < wend;
+            uint32_t exw = 0, wtot = 0;
+            if (any || boundary_inside) {
+                sts128(stash_s + 16 + 16 * lane, cur);
+                __syncwarp();
+                if (CP) exw = warp_excl_scan(wc, lane, &wtot);
+            }
+            // continuation bytes in [wbase, pos), pos in [wbase, wbase + 512]; uniform control flow
+            auto cont_upto = [&](int64_t pos) -> uint32_t {
+                const uint32_t rel = (uint32_t)(pos - wbase);
+                const uint32_t L = min(rel >> 4, 31u);
+                const uint32_t before = __shfl_sync(0xffffffffu, exw, L);
+                return before + cont_prefix(stash_s + 16 + 16 * L, rel - 16 * L);
+            };
+            if (any) {
+                // ---- stage 1: the survivors of the first probe, per lane ----
+                uint32_t m2 = 0;
+                for (uint32_t m = m1; m;) {
+                    const int k = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int i = 16 * (int)lane + k;
+                    uint32_t klo, khi;
+                    stash_key(i, klo, khi);
+                    uint32_t x = klo + khi * kMixHi;
+                    if (!sec_has(x)) continue;
+                    uint32_t d = W;
+                    bool go = false;
+                    for (;;) {
+                        if (d >= sv.last_level && sv.max_pat_len > sv.last_level) {
+                            go = true;  // patterns longer than this are not on chip (nor are this level's end marks)
+                            break;
+                        }
+                        if (sec_has(x ^ kSaltTerm)) {
+                            go = true;  // a pattern of length d may end here
+                            break;
+                        }
+                        if (d >= sv.last_level) break;
+                        const uint32_t b = lds8(stash_s + 16 + (uint32_t)(i - (int)d));  // the byte before the d-byte suffix
+                        x = sieve_step(x, b);
+                        d++;
+                        if (!sec_has(x)) break;
+                    }
+                    if (go) m2 |= 1u << k;
+                }
+                // ---- stage 2: exact verification, in stream order, one position per lane and round ----
+                uint32_t tot2;
+                const uint32_t ex2 = warp_excl_scan(__popc(m2), lane, &tot2);
+                for (uint32_t base = 0; base < tot2; base += 32) {
+                    const uint32_t g = base + lane;
+                    const bool active = g < tot2;
+                    uint32_t L = 0;
+#pragma unroll
+                    for (int step = 16; step >= 1; step >>= 1) {
+                        const uint32_t c = L + step;
+                        const uint32_t v = __shfl_sync(0xffffffffu, ex2, c & 31);
+                        if (c < 32 && v <= g) L = c;
+                    }
+                    const uint32_t mL = __shfl_sync(0xffffffffu, m2, L), exL = __shfl_sync(0xffffffffu, ex2, L);
+                    int k = 0;
+                    if (active) k = (int)__fns(mL, 0, (int)(g - exL) + 1);
+                    const int i = 16 * (int)L + k;
+                    const int64_t p = wbase + i;  // last byte of the candidate; the match would end at e = p + 1
+                    int64_t hs;
+                    const int64_t h = hay_of(active ? p : max(wbase, lo), hs);
+                    uint32_t best = kSieveNoNode, cnt = 0;
+                    if (active && p - (int64_t)(W - 1) >= hs) {
+                        uint32_t klo, khi;
+                        stash_key(i, klo, khi);
+                        const uint32_t x = klo + khi * kMixHi;
+                        uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
+                        uint32_t v = kSieveNoNode;
+                        for (;;) {
+                            const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
+                            if (ent.z == kSieveNoNode) break;
+                            if (ent.x == klo && ent.y == khi) {
+                                v = ent.z;
+                                break;
+                            }
+                            s = (s + 1) & (sv.ht_size - 1);
+                        }
+                        // walk towards the pattern start: node v = the d bytes before e
+                        uint32_t d = W;
+                        uint2 na = make_uint2(0, 0);
+                        if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
+                        while (v != kSieveNoNode) {
+                            if (na.y & kNodeTerminal) best = v;
+                            const uint32_t nk = (na.y >> 8) & 0x1ffu;
+                            if (nk == 0 || p - (int64_t)d < hs) break;  // no longer pattern, or it would start before the haystack
+                            const uint32_t b = __ldg(B.bytes + (p - (int64_t)d));
+                            uint32_t c = kSieveNoNode;
+                            uint2 nc = make_uint2(0, 0);
+                            if (nk <= 8) {
+                                for (uint32_t t = 0; t < nk; t++) {
+                                    const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
+                                    const uint32_t cb = cand.y & 0xffu;
+                                    if (cb >= b) {
+                                        if (cb == b) {
+                                            c = na.x + t;
+                                            nc = cand;
+                                        }
+                                        break;
+                                    }
+                                }
+                            } else {
+                                uint32_t l0 = 0, l1 = nk;  // first child with byte >= b
+                                while (l0 < l1) {
+                                    const uint32_t mid = (l0 + l1) >> 1;
+                                    if ((__ldg(&sv.na[na.x + mid].meta) & 0xffu) < b)
+                                        l0 = mid + 1;
+                                    else
+                                        l1 = mid;
+                                }
+                                if (l0 < nk) {
+                                    const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + l0));
+                                    if ((cand.y & 0xffu) == b) {
+                                        c = na.x + l0;
+                                        nc = cand;
+                                    }
+                                }
+                            }
+                            v = c;
+                            na = nc;
+                            d++;
+                        }
+                        if (best != kSieveNoNode) cnt = __ldg(&sv.nb[best].chain_cnt);
+                    }
+                    uint32_t total;
+                    const uint32_t exc = warp_excl_scan(cnt, lane, &total);
+                    if (total == 0) continue;
+                    // code points: continuation bytes between the counting origin of the match's haystack and its end
+                    uint32_t aux = 0;
+                    if (CP) {
+                        const uint32_t before = __reduce_add_sync(0xffffffffu, cp_lane);
+                        const int64_t e = (active ? p : wbase) + 1;
+                        const uint32_t upto_e = cont_upto(e);
+                        const bool inside = hs >= wbase;  // the haystack starts inside this window
+                        const uint32_t upto_hs = cont_upto(inside ? hs : wbase);
+                        aux = inside ? upto_e - upto_hs : before + upto_e - (h == h_prev ? cp_base : 0u);
+                    }
+                    unsigned long long rbase = 0;
+                    if (lane == 0) rbase = atomicAdd(out.raw_total, (unsigned long long)total);
+                    rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                    if (cnt) {
+                        unsigned long long idx = rbase + exc;
+                        uint32_t seq = n_emitted + exc;
+                        const uint32_t end_rel = (uint32_t)(p + 1 - hs);
+                        for (uint32_t u = best; u != kSieveNoNode;) {
+                            const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(sv.nb + u));  // own_off, own_cnt, term_link, depth
+                            for (uint32_t t = 0; t < nb.y; t++, idx++, seq++) {
+                                if (idx < out.cap) {
+                                    const uint32_t pid = __ldg(sv.pids + nb.x + t);
+                                    reinterpret_cast<uint4 *>(out.raw)[idx] = make_uint4((uint32_t)h, pid, end_rel - nb.w, end_rel);
+                                    out.raw_seq[idx] = seq;
+                                    out.raw_unit[idx] = task;
+                                    if (CP) out.raw_aux[idx] = aux;
+                                }
+                            }
+                            u = nb.z;
+                        }
+                    }
+                    n_emitted += total;
+                }
+            }
+            if (CP) {
+                // the haystack holding the last byte of this window becomes "the haystack before the next window"
+                int64_t hs_end;
+                const int64_t h_end = hay_of(wend - 1, hs_end);
+                if (h_end != h_prev) {
+                    const uint32_t before = __reduce_add_sync(0xffffffffu, cp_lane);
+                    cp_base = before + cont_upto(max(hs_end, wbase));
+                    h_prev = h_end;
+                }
+                cp_lane += wc;
+            }
+            if (wbase >= wlast) break;
+            __syncwarp();  // every lane is done with the stash before its history is replaced
+            if (lane == 31) sts128(stash_s, cur);
+            carry_z = __shfl_sync(0xffffffffu, cur.z, 31);
+            carry_w = __shfl_sync(0xffffffffu, cur.w, 31);
+            cur = nx1;
+            nx1 = nx2;
+        }
+        if (lane == 0) out.unit_counts[task] = n_emitted;
+        if (CP) {
+            const uint32_t all = __reduce_add_sync(0xffffffffu, cp_lane);
+            if (lane == 0) cont_tail[task] = all - cp_base;
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace acb

@@ -122,6 +122,7 @@ class _Automaton:
         self.num_columns = int(L.acb_num_columns(h))
         self.max_pattern_len = int(L.acb_max_pattern_len(h))
         self._images = {}      # device index -> uint8 tensor
+        self._sieves = {}      # device index -> (uint8 tensor, SieveDesc)
         self._hot = {}         # device index -> dict(tensor, rows, reprofile, calls, backoff)
         self._ws = {}          # device index -> dict of tensors
         self.last_stats = {}
@@ -148,6 +149,32 @@ class _Automaton:
             img = host.to(torch.device("cuda", idx), non_blocking=False)
             self._images[idx] = img
         return img
+
+    # ---- the sieve image (position-parallel scan: Bloom filter in shared memory + reverse trie in HBM/L2) ----
+    ENGINE = __import__("os").environ.get("ACB200_ENGINE", "sieve")   # "sieve" | "table": default kernel family
+    SIEVE_SMEM_RESERVE = 24 * 1024   # per-warp stashes, barrier, and some L1 left for the verification's loads
+    SIEVE_W_MAX = 0                  # 0 = the builder chooses the primary window
+
+    def sieve(self, device):
+        """(device tensor, SieveDesc) of the sieve image on `device`, built and uploaded once."""
+        torch = _require_cuda()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        ent = self._sieves.get(idx)
+        if ent is None:
+            props = torch.cuda.get_device_properties(idx)
+            smem = int(getattr(props, "shared_memory_per_block_optin", 227 * 1024))
+            nbytes = int(self._L.acb_sieve_build(self._h, max(4096, smem - self.SIEVE_SMEM_RESERVE), self.SIEVE_W_MAX))
+            if nbytes == 0:
+                raise RuntimeError(_capi.last_error())
+            host = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+            if self._L.acb_sieve_write(self._h, host.data_ptr(), nbytes) != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            desc = _capi.SieveDesc()
+            if self._L.acb_sieve_describe(host.data_ptr(), C.byref(desc)) != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            ent = (host.to(torch.device("cuda", idx)), desc)
+            self._sieves[idx] = ent
+        return ent
 
     # ---- the hot image (rows kept in shared memory), chosen from a sample of the data ----
     HOT_TABLE_BYTES = 40 * 1024   # with 32 warps of staging buffers next to it, this is what fits on chip
@@ -176,7 +203,7 @@ class _Automaton:
         exponential back-off -- when the kernel reports that the fast path keeps
         falling out of the hot set (the data changed character)."""
         torch = _torch()
-        idx = device.index
+        idx = device.index if device.index is not None else torch.cuda.current_device()
         st = self._hot.get(idx)
         need = st is None or st["reprofile"]
         if need and data is not None and data.numel() > 0 and offsets is not None and offsets.numel() > 1:
@@ -226,7 +253,7 @@ class _Automaton:
 
     def _workspace(self, device, plan, n_haystacks: int, capacity: int):
         torch = _torch()
-        idx = device.index
+        idx = device.index if device.index is not None else torch.cuda.current_device()
         ws = self._ws.get(idx)
         need = (ws is None or ws["n_units"] < plan.n_units or ws["n_segments"] < plan.n_segments or
                 ws["scratch"].numel() < plan.scratch_words or ws["n_haystacks"] < n_haystacks or ws["capacity"] < capacity)
@@ -297,13 +324,23 @@ class _Automaton:
         img = self.image(dev)
         cap = capacity or max(1024, n * 2)
         stream = torch.cuda.current_stream(dev).cuda_stream
+        # which kernel family: the position-parallel sieve (default) or the table walkers (forced by the tuning knob,
+        # or ENGINE = "table").  Results are identical; only the device images a scan needs differ.
+        forced = _capi.current_kernel()
+        use_sieve = forced == 5 or (forced == 0 and self.ENGINE == "sieve")
         with self._lock, torch.cuda.device(dev):
-            hot = self.hot(dev, data, offsets, overlapping)
+            if use_sieve:
+                sieve_t, sieve_d = self.sieve(dev)
+                hot = None
+            else:
+                hot = self.hot(dev, data, offsets, overlapping)
             plan = self._plan(data, n)
             while True:
                 ws = self._workspace(dev, plan, n, cap)
                 st = self._ws_struct(ws)
-                rc = self._L.acb_scan_batch(self._h, img.data_ptr(), hot["tensor"].data_ptr(), C.byref(hot["rows"]),
+                rc = self._L.acb_scan_batch(self._h, img.data_ptr(),
+                                            hot["tensor"].data_ptr() if hot else None, C.byref(hot["rows"]) if hot else None,
+                                            sieve_t.data_ptr() if use_sieve else None,
                                             data.data_ptr(), offsets.data_ptr(), n, data.numel(),
                                             int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
@@ -313,12 +350,18 @@ class _Automaton:
                     return ws["out"], ws["match_offsets"][: n + 1], ws["total"]
                 tot = ws["total"].tolist()
                 total, complete, raw_total = tot[0], tot[1], tot[4]
-                self._note_trap_stats(hot, tot[2], tot[3])
-                self.last_stats = {"groups": tot[2], "traps": tot[3], "repairs": tot[5], "segments": plan.n_segments,
-                                   "hot_rows": hot["rows"].rows, "hot_rows128": hot["rows"].rows128,
-                                   "hot_visited": hot["rows"].visited, "hot_coverage": round(hot.get("coverage", 1.0), 5),
-                                   "global_table": bool(hot["rows"].reserved & 1),
-                                   "segment_bytes": plan.segment_bytes, "lane_stride": plan.lane_stride}
+                if hot:
+                    self._note_trap_stats(hot, tot[2], tot[3])
+                    self.last_stats = {"engine": "table", "groups": tot[2], "traps": tot[3], "repairs": tot[5], "segments": plan.n_segments,
+                                       "hot_rows": hot["rows"].rows, "hot_rows128": hot["rows"].rows128,
+                                       "hot_visited": hot["rows"].visited, "hot_coverage": round(hot.get("coverage", 1.0), 5),
+                                       "global_table": bool(hot["rows"].reserved & 1),
+                                       "segment_bytes": plan.segment_bytes, "lane_stride": plan.lane_stride}
+                else:
+                    self.last_stats = {"engine": "sieve", "window": sieve_d.window, "last_level": sieve_d.last_level,
+                                       "probes": sieve_d.probes, "bloom_bytes": sieve_d.bloom_bytes, "nodes": sieve_d.nodes,
+                                       "keys": sieve_d.keys, "filter_entries": sieve_d.filter_entries,
+                                       "task_bytes": plan.task_bytes, "list_records": raw_total}
                 if complete or (total == 0 and raw_total == 0):
                     return ws["out"][:total], ws["match_offsets"][: n + 1], total
                 cap = max(total, raw_total) + max(total, raw_total) // 8 + 16

@@ -202,9 +202,7 @@ def main():
 
     L = _capi.lib()
     if args.segment_bytes or args.hot_rows or args.table or args.kernel:
-        import ctypes
-        t = _capi.Tuning(args.kernel, args.hot_rows, args.segment_bytes, args.table)
-        L.acb_set_tuning(ctypes.byref(t))
+        _capi.set_tuning(args.kernel, args.hot_rows, args.segment_bytes, args.table)
     n_hay = args.haystacks
     # two different batches per rank (rank r owns haystack indices [r*2*n, (r+1)*2*n)): weak scaling
     batches = []

@@ -124,6 +124,34 @@ typedef struct acb_hot_desc {
 int acb_hot_describe(const void *host_hot, acb_hot_desc *desc);
 
 /*
+ * The sieve image: the position-parallel form of the matcher (csrc/sieve.h).  Instead of walking an automaton -- one
+ * DEPENDENT table load per haystack byte -- every byte position is tested independently: the W bytes ending there are
+ * hashed into a Bloom filter of the patterns' suffixes held in shared memory; survivors walk on through the filter's
+ * deeper levels and are finally verified, exactly, against a reverse trie in global memory / L2, which names every
+ * pattern ending at that position in the reference's order.  That is the overlapping match list
+ * (try_find_overlapping_iter, src/lib.rs:52-54); the non-overlapping lists (try_find_iter, src/lib.rs:58-60) are
+ * selected from it per haystack for all three match kinds.  This is the compact (non-DFA) table format: a few tens of
+ * bytes per trie node instead of a dense row per state.
+ * acb_sieve_build builds (or rebuilds, when the arguments change) the image on the host and returns its size (0 on
+ * error): bloom_bytes_max = shared memory the filter may take (the caller knows the device), w_max = cap on the primary
+ * window in bytes (0 = automatic).  The caller uploads acb_sieve_write()'s copy and passes the device pointer to the
+ * scans as dev_sieve (NULL = use the table kernels).
+ */
+uint64_t acb_sieve_build(acb_automaton *a, uint32_t bloom_bytes_max, uint32_t w_max);
+int acb_sieve_write(acb_automaton *a, void *host_dst, uint64_t dst_bytes);
+typedef struct acb_sieve_desc {
+    uint32_t window;         /* W: bytes hashed per position by the fast path */
+    uint32_t last_level;     /* longest suffix length held by the on-chip filter */
+    uint32_t probes;         /* Bloom probes per key */
+    uint32_t bloom_bytes;
+    uint32_t nodes;          /* reverse-trie nodes (depth >= W) */
+    uint32_t keys;           /* distinct W-byte suffixes = hash table entries */
+    uint32_t filter_entries;
+    uint32_t table_slots;
+} acb_sieve_desc;
+int acb_sieve_describe(const void *host_sieve, acb_sieve_desc *desc);
+
+/*
  * How a scan is cut up.  The byte stream [offsets[0], offsets[n]) is divided into
  * fixed-size SEGMENTS on a grid anchored at the 64-byte aligned address at or
  * before dev_bytes; one GPU lane scans one segment, so the work per lane is the
@@ -141,7 +169,7 @@ typedef struct acb_plan {
     uint32_t segment_bytes;
     uint32_t warm_bytes;    /* bytes scanned before a segment to guess its start state (>= longest pattern) */
     uint32_t lane_stride;   /* segments between neighbouring lanes of a warp */
-    uint32_t reserved;
+    uint32_t task_bytes;    /* the sieve kernel's unit of work: bytes of the stream one warp walks (a multiple of 512) */
 } acb_plan;
 
 int acb_plan_scan(const acb_automaton *a, const void *dev_bytes, uint64_t total_bytes, uint64_t n_haystacks,
@@ -190,7 +218,7 @@ typedef struct acb_workspace {
  * byte is read, like the reference.
  */
 int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, const acb_hot_desc *hot_desc,
-                   const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
+                   const void *dev_sieve, const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
                    int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream);
 
 /* Kernel launch bookkeeping for bench.py's "gpu_launches". */
@@ -205,12 +233,13 @@ uint64_t acb_launch_count(void);
 int acb_timing_enable(int on);
 int acb_timing_read(double *total_ms, uint64_t *n_scans);
 
-/* Tuning knobs (0 = library default). Affects speed only, never results. */
+/* Tuning knobs (0 = library default), per calling thread. Affects speed only, never results. */
 typedef struct acb_tuning {
-    int kernel;        /* 0 auto, 1 = plain (one thread per haystack, table in global/L2), 2 = staged segments (hot rows in
-                          shared memory), 3 = staged, two segments per lane, 4 = segments straight from global/L2 */
+    int kernel;        /* 0 auto (the sieve when dev_sieve is given), 1 = plain (one thread per haystack, table in global/L2),
+                          2 = staged segments (hot rows in shared memory), 3 = staged, two segments per lane, 4 = segments
+                          straight from global/L2, 5 = sieve (position-parallel filter + exact verification) */
     int hot_rows;      /* cap on rows kept in shared memory */
-    int segment_bytes; /* segment size (rounded up to a multiple of 64 and to 8 x the warm-up) */
+    int segment_bytes; /* segment size (rounded up to a multiple of 64 and to 8 x the warm-up); kernel 5: task size (multiple of 512) */
     int table;         /* 0 auto, 1 = column-indexed compact table only, 2 = byte-indexed 128-wide table when available */
 } acb_tuning;
 int acb_set_tuning(const acb_tuning *t);

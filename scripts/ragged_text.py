@@ -24,4 +24,4 @@ for name, lens in [("equal 4096", np.full(100_000, 4096)), ("uniform 2048..4096"
     for _ in range(20): ac.scan_device(d, od, capacity=cap, sync=False)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 20
-    print(f"{name}: {len(flat)/1e6:.0f} MB, {total} matches, {ms:.3f} ms/step, {len(flat)/ms/1e6:.0f} GB/s, lane_stride {ac._ac.last_stats['lane_stride']}", flush=True)
+    print(f"{name}: {len(flat)/1e6:.0f} MB, {total} matches, {ms:.3f} ms/step, {len(flat)/ms/1e6:.0f} GB/s, engine {ac._ac.last_stats.get('engine')}", flush=True)

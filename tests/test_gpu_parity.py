@@ -24,14 +24,17 @@ with open(os.path.join(HERE, "golden", "reference_vectors.json"), encoding="utf-
 
 
 def set_kernel(kernel=0, hot_rows=0, segment_bytes=0, table=0):
-    t = _capi.Tuning(kernel, hot_rows, segment_bytes, table)
-    assert _capi.lib().acb_set_tuning(C.byref(t)) == 0
+    _capi.set_tuning(kernel, hot_rows, segment_bytes, table)
 
 
-@pytest.fixture(params=["staged", "plain", "staged-tiny-hot", "staged-small-segments", "staged-compact-table",
+@pytest.fixture(params=["sieve", "sieve-small-tasks", "staged", "plain", "staged-tiny-hot", "staged-small-segments", "staged-compact-table",
                         "staged-byte-table", "staged-byte-table-tiny", "staged-two-per-lane", "staged-two-per-lane-tiny", "global-segments", "global-small-segments"])
 def kernel(request):
-    if request.param == "plain":
+    if request.param == "sieve":
+        set_kernel(5)                 # the default engine: position-parallel filter + exact verification (scan_sieve.cuh)
+    elif request.param == "sieve-small-tasks":
+        set_kernel(5, 0, 512)         # one 512-byte window per task: every boundary case at every task start
+    elif request.param == "plain":
         set_kernel(1)
     elif request.param == "staged":
         set_kernel(2)                 # the default: compact (column-indexed) table, one segment per lane
@@ -168,7 +171,7 @@ def test_one_large_haystack_non_overlapping(kind, kernel):
     assert len(exp) > 10_000
     ac = BytesAhoCorasick(pats, kind)
     assert ac.find_matches_as_indexes(data.tobytes()) == exp
-    if kernel != "plain":
+    if kernel not in ("plain", "sieve", "sieve-small-tasks"):
         assert ac._ac.last_stats["segments"] > 1000
 
 
