@@ -362,7 +362,8 @@ struct SieveEpiArgs {
     uint32_t *unit_counts;               // [n_tasks] from the scan; later [n_haystacks] selected per haystack
     uint64_t n_tasks;
     unsigned long long *tile_sums, *unit_offsets;  // unit_offsets: [n_tasks + 1]; later [n_haystacks] first record of each haystack
-    const uint32_t *cont_tail;           // [n_tasks] (code points)
+    const uint32_t *cont_tail;           // [n_tasks] (code points): continuation bytes in each task
+    const uint32_t *hay_cont;            // [n_haystacks] (code points): continuation bytes between the start of the task a haystack starts in and the haystack
     unsigned long long *cont_tiles, *cont_cum;
     const acb_match *raw;
     const uint32_t *raw_seq, *raw_unit, *raw_aux;
@@ -463,25 +464,41 @@ __global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiAr
             if (dst >= E.out_cap) continue;
             uint4 r = reinterpret_cast<const uint4 *>(E.raw)[i];  // haystack, pattern, start, end (bytes)
             if (CP) {
-                unsigned long long cont = E.raw_aux[i];
+                // continuation bytes between the haystack's start and the match's end: both counts are relative to
+                // the start of the task they were taken in, cont_cum carries them to a common origin
                 const int64_t hs = E.B.offsets[r.x];
-                const int64_t t_lo = E.origin + (int64_t)u * (int64_t)E.task_bytes;
-                if (hs < t_lo) {
-                    // the haystack began in an earlier task: add what the tasks in between counted
-                    const int64_t u0 = (hs - E.origin) / (int64_t)E.task_bytes;
-                    cont += E.cont_cum[u] - E.cont_cum[u0];
-                }
+                const int64_t u0 = (hs - E.origin) / (int64_t)E.task_bytes;
+                const unsigned long long cont = (E.cont_cum[u] + E.raw_aux[i]) - (E.cont_cum[u0] + E.hay_cont[r.x]);
                 const uint32_t end_cp = r.w - (uint32_t)cont;
                 r.w = end_cp;
                 r.z = end_cp - E.pat_cplen[r.y];
             }
             reinterpret_cast<uint4 *>(E.ordered)[dst] = r;
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) E.totals[6] = E.unit_offsets[E.n_tasks];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            E.totals[6] = E.unit_offsets[E.n_tasks];
+            E.totals[7] = E.acc[kAccRaw];
+        }
     }
     grid.sync();
     const unsigned long long list_total = E.totals[6];
     const unsigned long long avail = list_total < E.out_cap ? list_total : E.out_cap;
+    if (MODE != kModeOverlap && (list_total > E.out_cap || E.totals[7] > E.raw_cap)) {
+        // The buffers were too small: the ordered list has holes (stale records), nothing may be selected from it.
+        // Report how much room is needed; the caller retries.  (Every block takes this branch: totals[6..7] were
+        // published before the barrier and nobody writes them again.)
+        for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) E.match_offsets[h] = 0;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const unsigned long long raw_total = E.totals[7];
+            E.totals[0] = list_total;
+            E.totals[1] = 0;
+            E.totals[2] = E.totals[3] = E.totals[5] = 0;
+            E.totals[4] = raw_total > list_total ? raw_total : list_total;
+            E.acc[kAccRaw] = E.acc[kAccGroups] = E.acc[kAccTraps] = E.acc[kAccRepairs] = 0;
+            E.acc[kAccQueue] = 0;
+        }
+        return;
+    }
     if (MODE == kModeOverlap) {
         for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x)
             E.match_offsets[h] = (h == E.B.n_haystacks) ? list_total : first_of_haystack(E.ordered, avail, h);
@@ -934,19 +951,26 @@ DevSieve make_sieve_view(const SieveHeader &h, const void *dev_sieve) {
     v.prim_words = h.prim_words;
     v.ht_size = h.ht_mask + 1;
     v.max_pat_len = h.max_pat_len;
+    v.term_levels = h.term_levels;
     return v;
 }
 
 template <bool CP>
-int launch_sieve(const DevSieve &sv, const Batch &B, const SievePlan &P, const Sink &out, uint32_t *cont_tail, unsigned int *task_counter,
-                 const DeviceInfo &d, cudaStream_t st) {
-    const uint32_t smem = sv.bloom_words * 4 + kSieveSmemFixed;
-    if ((int)smem > d.max_smem_optin) return fail(ACB_ECUDA, "the sieve's filter does not fit in shared memory (rebuild it with a smaller bloom_bytes_max)");
+int launch_sieve(const DevSieve &sv, const Batch &B, SievePlan &P, const Sink &out, uint32_t *task_cont, uint32_t *hay_cont,
+                 unsigned int *task_counter, const DeviceInfo &d, cudaStream_t st) {
+    // as many windows of text per warp as fit next to the filters (a power of two): the more, the fuller the rounds of
+    // the later stages when survivors are rare
+    const uint32_t filter_bytes = sv.bloom_words * 4;
+    uint32_t ring = kRingMax;
+    while (ring > 1 && sieve_smem_bytes(filter_bytes, ring, CP) > (uint32_t)d.max_smem_optin) ring >>= 1;
+    const uint32_t smem = sieve_smem_bytes(filter_bytes, ring, CP);
+    if (smem > (uint32_t)d.max_smem_optin) return fail(ACB_ECUDA, "the sieve's filters do not fit in shared memory (rebuild them with a smaller bloom_bytes_max)");
+    P.ring = ring;
 #define ACB_SIEVE_GO(WC)                                                                                  \
     do {                                                                                                  \
         auto kern = sieve_scan_kernel<CP, WC>;                                                            \
         CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, d.max_smem_optin)); \
-        kern<<<d.sms, kSieveThreads, smem, st>>>(sv, B, P, out, cont_tail, task_counter);                 \
+        kern<<<d.sms, kSieveThreads, smem, st>>>(sv, B, P, out, task_cont, hay_cont, task_counter);       \
     } while (0)
     if (sv.W < 4)
         ACB_SIEVE_GO(0);
@@ -1100,8 +1124,11 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
             CUDA_OK(cudaEventCreate(&e1));
             CUDA_OK(cudaEventRecord(e0, st));
         }
-        rc = cp ? launch_sieve<true>(sv, B, SP, out, cont_tail, task_counter, d, st)
-                : launch_sieve<false>(sv, B, SP, out, cont_tail, task_counter, d, st);
+        // code points: the continuation bytes each task saw before a haystack that starts in it, per haystack; lives in
+        // the match_offsets buffer until the epilogue's last phases write the offsets there
+        uint32_t *hay_cont = reinterpret_cast<uint32_t *>(match_offsets);
+        rc = cp ? launch_sieve<true>(sv, B, SP, out, cont_tail, hay_cont, task_counter, d, st)
+                : launch_sieve<false>(sv, B, SP, out, cont_tail, hay_cont, task_counter, d, st);
         if (rc) return rc;
         CUDA_OK(cudaGetLastError());
         if (e1) {
@@ -1115,6 +1142,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
         E.tile_sums = tile_sums;
         E.unit_offsets = unit_offsets;
         E.cont_tail = cont_tail;
+        E.hay_cont = hay_cont;
         E.cont_tiles = cont_tiles;
         E.cont_cum = cont_cum;
         E.raw = out.raw;

@@ -3,9 +3,11 @@
 // One persistent CTA per SM, 32 warps.  Dynamic shared memory:
 //   [ primary bitmap | secondary Bloom filter : bloom_words x u32 ]   one TMA bulk copy (cp.async.bulk + mbarrier)
 //   [ mbarrier ]
-//   [ per warp: 16 B history | 512 B window | 16 B pad ]   the "stash": the text the warp is looking at, for the
-//        few positions that survive the first probe (their hash is recomputed from here, the on-chip walk reads
-//        older bytes from here); written only when a window has survivors
+//   [ per warp: R x (16 B history | 512 B window) | 16 B pad ]   the "stash": a ring of the last R windows of text the
+//        warp looked at, for the few positions that survive the first probe (their hash is recomputed from here, the
+//        on-chip walk reads older bytes from here); a window is written only when it has survivors
+//   [ per warp: two queues of 64 positions ]   survivors of the first probe waiting for stage 1, survivors of stage 1
+//        waiting for stage 2: the later stages run 32 positions at a time (one per lane) whatever window they came from
 //
 // Work: the byte stream is cut into TASKS of task_bytes (a multiple of 512) on a grid anchored at a 512-byte aligned
 // address; warps claim tasks from an atomic counter and walk them in 512-byte WINDOWS: lane l holds bytes
@@ -16,13 +18,15 @@
 //               the two words before them, which come from the neighbouring lane), hashes it (one IMAD; two for W > 4)
 //               and tests ONE bit of the filter: IMAD.HI (word) + LEA + LDS + SHF (bit) + SHF (collect).  No chain,
 //               no branch: 16 independent probes per lane.
-//   stage 1     lanes with survivors (a few % of positions) redo them from the stash: remaining probes, then the
-//               on-chip walk towards the pattern start through the deeper filter levels.  What is left needs the
-//               exact check.
-//   stage 2     those positions, in stream order, 32 at a time (one per lane): hash table -> reverse-trie walk in global
-//               memory / L2 -> the deepest terminal node = every pattern ending there; matches are written with ONE
-//               atomicAdd per round (warp-aggregated reservation; ranks by shuffle prefix sums), each tagged with
-//               (task, rank in task) so that the epilogue can place it without a sort.
+//   queueing    survivors (a few % of positions) are appended, in stream order, to the warp's first queue (ballot /
+//               prefix sums over the lanes' hit masks).
+//   stage 1     whenever 32 positions are waiting (or their text is about to leave the ring): one position per lane --
+//               the hash is recomputed from the stash, the second filter is probed, then the on-chip walk towards the
+//               pattern start through the deeper filter levels.  What is left goes to the second queue.
+//   stage 2     the same way, 32 at a time: hash table -> reverse-trie walk in global memory / L2 -> the deepest terminal
+//               node = every pattern ending there; matches are written with ONE atomicAdd per round (warp-aggregated
+//               reservation; ranks by shuffle prefix sums), each tagged with (task, rank in task) so that the epilogue
+//               can place it without a sort.  Both queues are first-in first-out, so matches leave in stream order.
 //
 // Output of this kernel = the OVERLAPPING match list.  sieve_epilogue_kernel (capi.cu) orders it and, for the
 // non-overlapping searches, selects from it per haystack.
@@ -35,8 +39,14 @@ namespace acb {
 constexpr int kSieveWarps = 32;
 constexpr int kSieveThreads = kSieveWarps * 32;
 constexpr uint32_t kWin = 512;                       // bytes per warp window
-constexpr uint32_t kStashBytes = 16 + kWin + 16;     // per warp
-constexpr uint32_t kSieveSmemFixed = 16 + kSieveWarps * kStashBytes;  // mbarrier slot + stashes (after the filter)
+constexpr uint32_t kSlotBytes = 16 + kWin;           // one ring slot: 16 bytes of history, then the window
+constexpr uint32_t kQueueCap = 64;                   // positions per queue (a round takes 32; at most 32 arrive at a time)
+constexpr uint32_t kRingMax = 8;
+// per warp: ring | pad | two queues (entries: 4 bytes, or 8 with the code point count)
+__host__ __device__ constexpr uint32_t sieve_warp_bytes(uint32_t ring, bool cp) { return ring * kSlotBytes + 16 + 2 * kQueueCap * (cp ? 8u : 4u); }
+__host__ __device__ constexpr uint32_t sieve_smem_bytes(uint32_t filter_bytes, uint32_t ring, bool cp) {
+    return filter_bytes + 16 + kSieveWarps * sieve_warp_bytes(ring, cp);
+}
 
 struct DevSieve {
     const uint32_t *bloom;
@@ -44,7 +54,7 @@ struct DevSieve {
     const SieveNodeA *na;
     const SieveNodeB *nb;
     const uint32_t *pids;
-    uint32_t W, last_level, n_probes, bloom_words, prim_words, ht_size, max_pat_len;
+    uint32_t W, last_level, n_probes, bloom_words, prim_words, ht_size, max_pat_len, term_levels;
 };
 
 struct SievePlan {
@@ -53,6 +63,7 @@ struct SievePlan {
     uint64_t buf_bytes;  // length of the byte buffer (loads stay inside [0, buf_bytes))
     uint64_t avg_len;    // hint for the first haystack lookup of a task
     uint32_t task_bytes;
+    uint32_t ring;       // windows of text each warp keeps in shared memory (1..kRingMax)
 };
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
@@ -111,25 +122,28 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
 // WC: 0 = W < 4 (the window word is shifted down), 1 = W == 4, 2 = W in 5..8 (two words)
 template <bool CP, int WC>
 __global__ void __launch_bounds__(kSieveThreads, 1)
-sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_tail, unsigned int *task_counter) {
+sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_cont, uint32_t *hay_cont, unsigned int *task_counter) {
     extern __shared__ __align__(128) uint8_t smem[];
+    constexpr uint32_t QE = CP ? 8u : 4u;  // queue entry: position (relative to the task start) [, continuation bytes before its end]
     const uint32_t bloom_s = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t bloom_bytes = sv.bloom_words * 4;
     const uint32_t bar_s = bloom_s + bloom_bytes;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t stash_s = bar_s + 16 + warp * kStashBytes;  // history at +0, window at +16
-    const uint32_t n_words = sv.prim_words;                       // the primary bitmap (fast path)
-    const uint32_t sec_s = bloom_s + sv.prim_words * 4;           // the secondary filter
+    const uint32_t R = P.ring;  // a power of two
+    const uint32_t ring_s = bar_s + 16 + warp * sieve_warp_bytes(R, CP);
+    const uint32_t q1_s = ring_s + R * kSlotBytes + 16, q2_s = q1_s + kQueueCap * QE;
+    const uint32_t n_words = sv.prim_words;              // the primary bitmap (fast path)
+    const uint32_t sec_s = bloom_s + sv.prim_words * 4;  // the secondary filter
     const uint32_t sec_words = sv.bloom_words - sv.prim_words;
 
-    // ---- prologue: the filter ----------------------------------------------------------------
+    // ---- prologue: the filters ----------------------------------------------------------------
     if (threadIdx.x == 0) {
         mbar_init(bar_s, 1);
         mbar_expect_tx(bar_s, bloom_bytes);
         tma_bulk_g2s(bloom_s, sv.bloom, bloom_bytes, bar_s);
     }
-    // the pad behind each window stays zero (stage 1 reads one aligned word past the last byte)
-    if (lane < 4) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(stash_s + 16 + kWin + lane * 4), "r"(0u) : "memory");
+    // the pad behind the ring stays zero (a key read may touch one aligned word past the last slot)
+    if (lane < 4) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(ring_s + R * kSlotBytes + lane * 4), "r"(0u) : "memory");
     __syncthreads();
     mbar_wait(bar_s, 0);
 
@@ -145,9 +159,11 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_ta
         return (word >> (p & 31u)) & 1u;
     };
     auto sec_has = [&](uint32_t x) -> bool { return sec_bit(x * kMulB) && (sv.n_probes < 2 || sec_bit(x * kMulC)); };
-    // the 8 bytes ending at window-relative byte index i (inclusive), from the stash: (lo', hi') as the filter keys them
-    auto stash_key = [&](int i, uint32_t &klo, uint32_t &khi) {
-        const uint32_t a = stash_s + 16 + (uint32_t)(i - 7);  // i - 7 >= -16 + ... : history covers 16 bytes
+    // shared address of the byte at task-relative position rel (its window must still be in the ring)
+    auto text_s = [&](uint32_t rel) -> uint32_t { return ring_s + ((rel >> 9) & (R - 1)) * kSlotBytes + 16 + (rel & (kWin - 1)); };
+    // the 8 bytes ending at rel (inclusive), from the stash: (lo', hi') as the filters key them
+    auto stash_key = [&](uint32_t rel, uint32_t &klo, uint32_t &khi) {
+        const uint32_t a = text_s(rel) - 7;  // the slot's 16 bytes of history cover the reach
         const uint32_t j = a & ~3u, r = (a & 3u) * 8u;
         const uint32_t w0 = lds32v(j), w1 = lds32v(j + 4), w2 = lds32v(j + 8);
         const uint32_t hi = shf_r_wrap(w0, w1, r), lo = shf_r_wrap(w1, w2, r);
@@ -166,7 +182,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_ta
         if (lo >= hi) {
             if (lane == 0) {
                 out.unit_counts[task] = 0;
-                if (CP) cont_tail[task] = 0;
+                if (CP) task_cont[task] = 0;
             }
             continue;
         }
@@ -188,8 +204,9 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_ta
             return idx <= B.n_haystacks ? (uint32_t)__ldg(B.offsets + idx) : 0xffffffffu;
         };
         uint32_t offc = load_offc(hb);
-        // haystack containing byte p (p >= the first cached offset) and its start.  The shuffles are executed by the whole
-        // warp; a window with more than 31 haystack starts (haystacks of a few bytes) falls back to a search per lane.
+        // Haystack containing byte p, and its start.  The shuffles are executed by the whole warp (p may differ per lane).
+        // Positions before the cached range (queued in an earlier window) walk back from it; a window with more than
+        // 31 haystack starts (haystacks of a few bytes) falls back to a search.
         auto hay_of = [&](int64_t p, int64_t &hs) -> int64_t {
             uint32_t l = 0;
 #pragma unroll
@@ -200,25 +217,204 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_ta
             }
             hs = (int64_t)__shfl_sync(0xffffffffu, offc, l);
             int64_t h = hb + l;
-            if (l == 31 && h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= p) {
+            if (hs > p) {
+                // before the cache: the haystack is a few entries back
+                int64_t step = 1, below = hb;
+                while (below > 0 && __ldg(B.offsets + below) > p) {
+                    below = max(below - step, (int64_t)0);
+                    step <<= 1;
+                }
+                h = below;
+                while (h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= p) h++;  // last haystack that starts at or before p
+                hs = __ldg(B.offsets + h);
+            } else if (l == 31 && h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= p) {
                 h = find_haystack(B, p);
                 hs = __ldg(B.offsets + h);
             }
             return h;
         };
 
-        uint32_t n_emitted = 0;
-        // code points: continuation bytes seen by this lane in earlier windows of the task | count at the start of the
-        // haystack that holds the byte before the window (0 while that haystack began before the task)
-        uint32_t cp_lane = 0, cp_base = 0;
-        int64_t h_prev = hb;  // haystack holding the byte before the window (first window: the one holding `lo`)
+        uint32_t n_emitted = 0, q1n = 0, q2n = 0;
+        uint32_t cp_lane = 0;  // code points: continuation bytes seen by this lane in earlier windows of the task
+
+        // ---- stage 2: exact verification of the first (up to) 32 positions of the second queue ----
+        auto round2 = [&]() {
+            const uint32_t n = min(q2n, 32u);
+            const bool active = lane < n;
+            uint32_t rel = 0, aux = 0;
+            if (active) {
+                rel = lds32v(q2_s + lane * QE);
+                if (CP) aux = lds32v(q2_s + lane * QE + 4);
+            }
+            const int64_t p = t_lo + rel;  // last byte of the candidate; the match would end at e = p + 1
+            int64_t hs;
+            const int64_t h = hay_of(active ? p : max(wbase, lo), hs);
+            uint32_t best = kSieveNoNode, cnt = 0;
+            if (active && p - (int64_t)(W - 1) >= hs) {
+                uint32_t klo, khi;
+                stash_key(rel, klo, khi);
+                const uint32_t x = klo + khi * kMixHi;
+                uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
+                uint32_t v = kSieveNoNode;
+                for (;;) {
+                    const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
+                    if (ent.z == kSieveNoNode) break;
+                    if (ent.x == klo && ent.y == khi) {
+                        v = ent.z;
+                        break;
+                    }
+                    s = (s + 1) & (sv.ht_size - 1);
+                }
+                // walk towards the pattern start: node v = the d bytes before e
+                uint32_t d = W;
+                uint2 na = make_uint2(0, 0);
+                if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
+                while (v != kSieveNoNode) {
+                    if (na.y & kNodeTerminal) best = v;
+                    const uint32_t nk = (na.y >> 8) & 0x1ffu;
+                    if (nk == 0 || p - (int64_t)d < hs) break;  // no longer pattern, or it would start before the haystack
+                    const uint32_t b = __ldg(B.bytes + (p - (int64_t)d));
+                    uint32_t c = kSieveNoNode;
+                    uint2 nc = make_uint2(0, 0);
+                    if (nk <= 8) {
+                        for (uint32_t t = 0; t < nk; t++) {
+                            const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
+                            const uint32_t cb = cand.y & 0xffu;
+                            if (cb >= b) {
+                                if (cb == b) {
+                                    c = na.x + t;
+                                    nc = cand;
+                                }
+                                break;
+                            }
+                        }
+                    } else {
+                        uint32_t l0 = 0, l1 = nk;  // first child with byte >= b
+                        while (l0 < l1) {
+                            const uint32_t mid = (l0 + l1) >> 1;
+                            if ((__ldg(&sv.na[na.x + mid].meta) & 0xffu) < b)
+                                l0 = mid + 1;
+                            else
+                                l1 = mid;
+                        }
+                        if (l0 < nk) {
+                            const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + l0));
+                            if ((cand.y & 0xffu) == b) {
+                                c = na.x + l0;
+                                nc = cand;
+                            }
+                        }
+                    }
+                    v = c;
+                    na = nc;
+                    d++;
+                }
+                if (best != kSieveNoNode) cnt = __ldg(&sv.nb[best].chain_cnt);
+            }
+            uint32_t total;
+            const uint32_t exc = warp_excl_scan(cnt, lane, &total);
+            if (total) {
+                unsigned long long rbase = 0;
+                if (lane == 0) rbase = atomicAdd(out.raw_total, (unsigned long long)total);
+                rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                if (cnt) {
+                    unsigned long long idx = rbase + exc;
+                    uint32_t seq = n_emitted + exc;
+                    const uint32_t end_rel = (uint32_t)(p + 1 - hs);
+                    for (uint32_t u = best; u != kSieveNoNode;) {
+                        const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(sv.nb + u));  // own_off, own_cnt, term_link, depth
+                        for (uint32_t t = 0; t < nb.y; t++, idx++, seq++) {
+                            if (idx < out.cap) {
+                                const uint32_t pid = __ldg(sv.pids + nb.x + t);
+                                reinterpret_cast<uint4 *>(out.raw)[idx] = make_uint4((uint32_t)h, pid, end_rel - nb.w, end_rel);
+                                out.raw_seq[idx] = seq;
+                                out.raw_unit[idx] = task;
+                                if (CP) out.raw_aux[idx] = aux;
+                            }
+                        }
+                        u = nb.z;
+                    }
+                }
+                n_emitted += total;
+            }
+            // pop the round
+            uint2 keep = make_uint2(0, 0);
+            const bool mv = 32 + lane < q2n;
+            if (mv) {
+                keep.x = lds32v(q2_s + (32 + lane) * QE);
+                if (CP) keep.y = lds32v(q2_s + (32 + lane) * QE + 4);
+            }
+            __syncwarp();
+            if (mv) {
+                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + lane * QE), "r"(keep.x) : "memory");
+                if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + lane * QE + 4), "r"(keep.y) : "memory");
+            }
+            q2n -= n;
+            __syncwarp();
+        };
+
+        // ---- stage 1: second filter and the on-chip walk for the first (up to) 32 positions of the first queue ----
+        auto round1 = [&]() {
+            if (q2n > 32) round2();  // room for 32 survivors
+            const uint32_t n = min(q1n, 32u);
+            const bool active = lane < n;
+            uint32_t rel = 0, aux = 0;
+            bool go = false;
+            if (active) {
+                rel = lds32v(q1_s + lane * QE);
+                if (CP) aux = lds32v(q1_s + lane * QE + 4);
+                uint32_t klo, khi;
+                stash_key(rel, klo, khi);
+                uint32_t x = klo + khi * kMixHi;
+                if (sec_has(x)) {
+                    const uint32_t ta = text_s(rel);
+                    uint32_t d = W;
+                    for (;;) {
+                        if (d >= sv.last_level && sv.max_pat_len > sv.last_level) {
+                            go = true;  // patterns longer than this are not on chip (nor are this level's end marks)
+                            break;
+                        }
+                        if (((sv.term_levels >> d) & 1u) && sec_has(x ^ kSaltTerm)) {
+                            go = true;  // a pattern of length d may end here
+                            break;
+                        }
+                        if (d >= sv.last_level) break;
+                        const uint32_t b = lds8(ta - d);  // the byte before the d-byte suffix
+                        x = sieve_step(x, b);
+                        d++;
+                        if (!sec_has(x)) break;
+                    }
+                }
+            }
+            const uint32_t surv = __ballot_sync(0xffffffffu, go);
+            if (go) {
+                const uint32_t at = q2n + __popc(surv & ((1u << lane) - 1u));
+                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + at * QE), "r"(rel) : "memory");
+                if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + at * QE + 4), "r"(aux) : "memory");
+            }
+            q2n += __popc(surv);
+            // pop the round
+            uint2 keep = make_uint2(0, 0);
+            const bool mv = 32 + lane < q1n;
+            if (mv) {
+                keep.x = lds32v(q1_s + (32 + lane) * QE);
+                if (CP) keep.y = lds32v(q1_s + (32 + lane) * QE + 4);
+            }
+            __syncwarp();
+            if (mv) {
+                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + lane * QE), "r"(keep.x) : "memory");
+                if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + lane * QE + 4), "r"(keep.y) : "memory");
+            }
+            q1n -= n;
+            __syncwarp();
+        };
 
         uint32_t carry_z = 0, carry_w = 0;
         {
             const uint4 c = load_chunk(B.bytes, wbase - 16, vlo, vhi);
             carry_z = c.z;
             carry_w = c.w;
-            if (lane == 0) sts128(stash_s, c);
+            if (lane == 0) sts128(text_s((uint32_t)(wbase - t_lo)) - 16, c);
         }
         uint4 cur = load_chunk(B.bytes, wbase + 16 * lane, vlo, vhi);
         uint4 nx1 = make_uint4(0, 0, 0, 0), nx2 = make_uint4(0, 0, 0, 0);
@@ -258,218 +454,104 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *cont_ta
                 const int from = (int)min(max(plo - q, (int64_t)0), (int64_t)16), to = (int)min(max(hi - q, (int64_t)0), (int64_t)16);
                 m1 &= ((1u << to) - 1u) & ~((1u << from) - 1u);
             }
+            const uint32_t wrel = (uint32_t)(wbase - t_lo);  // this window, relative to the task
+            const int64_t wend = min(wbase + (int64_t)kWin, hi);  // one past the last stream byte of this window
+            // does the cached offset range still start at the haystack that holds this window's first byte?
+            if ((int64_t)__shfl_sync(0xffffffffu, offc, 1) <= wbase) {
+                const int64_t first = max(wbase, lo);
+                const uint32_t ahead = __popc(__ballot_sync(0xffffffffu, (int64_t)offc <= first));
+                hb = ahead == 32 ? find_haystack(B, first) : hb + ahead - 1;
+                offc = load_offc(hb);
+            }
             uint32_t wc = 0;  // code points: continuation bytes in this lane's chunk
+            bool starts_inside = false;
             if (CP) {
                 if ((cur.x | cur.y | cur.z | cur.w) & 0x80808080u) wc = cont_bytes(cur.x) + cont_bytes(cur.y) + cont_bytes(cur.z) + cont_bytes(cur.w);
+                // haystacks that START in this window record how many continuation bytes the task has seen before them
+                const int64_t o0 = (int64_t)__shfl_sync(0xffffffffu, offc, 0), o1 = (int64_t)__shfl_sync(0xffffffffu, offc, 1);
+                starts_inside = o0 >= max(wbase, lo) || o1 < wend;
             }
-            const int64_t wend = min(wbase + (int64_t)kWin, hi);  // one past the last stream byte of this window
-            // does the cached offset range still cover this window?  (31 haystack starts ahead at most)
-            bool refreshed = false;
-            {
-                const uint32_t o1 = __shfl_sync(0xffffffffu, offc, 1);
-                if ((int64_t)o1 <= wbase) {
-                    // the window starts beyond haystack hb: move the cache forward to the haystack holding max(wbase, lo)
-                    const int64_t first = max(wbase, lo);
-                    const uint32_t ahead = __popc(__ballot_sync(0xffffffffu, (int64_t)offc <= first));
-                    if (ahead == 32) {
-                        hb = find_haystack(B, first);
-                    } else {
-                        hb += ahead - 1;
-                    }
-                    offc = load_offc(hb);
-                    refreshed = true;
-                }
-            }
-            (void)refreshed;
             const bool any = __any_sync(0xffffffffu, m1 != 0);
-            // code points need the stash (and the prefix of wc) when a haystack starts inside the window, too
-            const uint32_t o1 = __shfl_sync(0xffffffffu, offc, 1);
-            const bool boundary_inside = CP && (int64_t)o1 < wend;
-            uint32_t exw = 0, wtot = 0;
-            if (any || boundary_inside) {
-                sts128(stash_s + 16 + 16 * lane, cur);
+            if (any || starts_inside) {
+                sts128(text_s(wrel) + 16 * lane, cur);
                 __syncwarp();
-                if (CP) exw = warp_excl_scan(wc, lane, &wtot);
-            }
-            // continuation bytes in [wbase, pos), pos in [wbase, wbase + 512]; uniform control flow
-            auto cont_upto = [&](int64_t pos) -> uint32_t {
-                const uint32_t rel = (uint32_t)(pos - wbase);
-                const uint32_t L = min(rel >> 4, 31u);
-                const uint32_t before = __shfl_sync(0xffffffffu, exw, L);
-                return before + cont_prefix(stash_s + 16 + 16 * L, rel - 16 * L);
-            };
-            if (any) {
-                // ---- stage 1: the survivors of the first probe, per lane ----
-                uint32_t m2 = 0;
-                for (uint32_t m = m1; m;) {
-                    const int k = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int i = 16 * (int)lane + k;
-                    uint32_t klo, khi;
-                    stash_key(i, klo, khi);
-                    uint32_t x = klo + khi * kMixHi;
-                    if (!sec_has(x)) continue;
-                    uint32_t d = W;
-                    bool go = false;
+                uint32_t exw = 0, wtot = 0, before = 0;
+                if (CP) {
+                    exw = warp_excl_scan(wc, lane, &wtot);
+                    before = __reduce_add_sync(0xffffffffu, cp_lane);
+                }
+                // continuation bytes in [lo, pos) for pos in [wbase, wbase + 512]; executed by the whole warp
+                auto cont_before = [&](int64_t pos) -> uint32_t {
+                    const uint32_t rl = (uint32_t)(pos - wbase);
+                    const uint32_t L = min(rl >> 4, 31u);
+                    const uint32_t ex = __shfl_sync(0xffffffffu, exw, L);
+                    if (wtot == 0) return before;  // (an ASCII window: nothing to add)
+                    return before + ex + cont_prefix(text_s(wrel) + 16 * L, rl - 16 * L);
+                };
+                if (CP && starts_inside) {
                     for (;;) {
-                        if (d >= sv.last_level && sv.max_pat_len > sv.last_level) {
-                            go = true;  // patterns longer than this are not on chip (nor are this level's end marks)
-                            break;
-                        }
-                        if (sec_has(x ^ kSaltTerm)) {
-                            go = true;  // a pattern of length d may end here
-                            break;
-                        }
-                        if (d >= sv.last_level) break;
-                        const uint32_t b = lds8(stash_s + 16 + (uint32_t)(i - (int)d));  // the byte before the d-byte suffix
-                        x = sieve_step(x, b);
-                        d++;
-                        if (!sec_has(x)) break;
+                        const int64_t s = (int64_t)offc;
+                        const bool mine = s >= max(wbase, lo) && s < wend && hb + lane < B.n_haystacks;
+                        const uint32_t c = cont_before(mine ? s : wbase);
+                        if (mine) hay_cont[hb + lane] = c;
+                        // more than 32 starts in one window: move the cache on and repeat
+                        if ((int64_t)__shfl_sync(0xffffffffu, offc, 31) >= wend || hb + 31 >= B.n_haystacks) break;
+                        hb += 31;
+                        offc = load_offc(hb);
                     }
-                    if (go) m2 |= 1u << k;
                 }
-                // ---- stage 2: exact verification, in stream order, one position per lane and round ----
-                uint32_t tot2;
-                const uint32_t ex2 = warp_excl_scan(__popc(m2), lane, &tot2);
-                for (uint32_t base = 0; base < tot2; base += 32) {
-                    const uint32_t g = base + lane;
-                    const bool active = g < tot2;
-                    uint32_t L = 0;
+                if (any) {
+                    // ---- queue this window's survivors, in stream order (lane i takes the (base + i)-th of them) ----
+                    uint32_t tot1;
+                    const uint32_t ex1 = warp_excl_scan(__popc(m1), lane, &tot1);
+                    for (uint32_t base = 0; base < tot1; base += 32) {
+                        const uint32_t g = base + lane;
+                        const bool active = g < tot1;
+                        uint32_t L = 0;
 #pragma unroll
-                    for (int step = 16; step >= 1; step >>= 1) {
-                        const uint32_t c = L + step;
-                        const uint32_t v = __shfl_sync(0xffffffffu, ex2, c & 31);
-                        if (c < 32 && v <= g) L = c;
-                    }
-                    const uint32_t mL = __shfl_sync(0xffffffffu, m2, L), exL = __shfl_sync(0xffffffffu, ex2, L);
-                    int k = 0;
-                    if (active) k = (int)__fns(mL, 0, (int)(g - exL) + 1);
-                    const int i = 16 * (int)L + k;
-                    const int64_t p = wbase + i;  // last byte of the candidate; the match would end at e = p + 1
-                    int64_t hs;
-                    const int64_t h = hay_of(active ? p : max(wbase, lo), hs);
-                    uint32_t best = kSieveNoNode, cnt = 0;
-                    if (active && p - (int64_t)(W - 1) >= hs) {
-                        uint32_t klo, khi;
-                        stash_key(i, klo, khi);
-                        const uint32_t x = klo + khi * kMixHi;
-                        uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
-                        uint32_t v = kSieveNoNode;
-                        for (;;) {
-                            const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
-                            if (ent.z == kSieveNoNode) break;
-                            if (ent.x == klo && ent.y == khi) {
-                                v = ent.z;
-                                break;
-                            }
-                            s = (s + 1) & (sv.ht_size - 1);
+                        for (int step = 16; step >= 1; step >>= 1) {
+                            const uint32_t c = L + step;
+                            const uint32_t v = __shfl_sync(0xffffffffu, ex1, c & 31);
+                            if (c < 32 && v <= g) L = c;
                         }
-                        // walk towards the pattern start: node v = the d bytes before e
-                        uint32_t d = W;
-                        uint2 na = make_uint2(0, 0);
-                        if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
-                        while (v != kSieveNoNode) {
-                            if (na.y & kNodeTerminal) best = v;
-                            const uint32_t nk = (na.y >> 8) & 0x1ffu;
-                            if (nk == 0 || p - (int64_t)d < hs) break;  // no longer pattern, or it would start before the haystack
-                            const uint32_t b = __ldg(B.bytes + (p - (int64_t)d));
-                            uint32_t c = kSieveNoNode;
-                            uint2 nc = make_uint2(0, 0);
-                            if (nk <= 8) {
-                                for (uint32_t t = 0; t < nk; t++) {
-                                    const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
-                                    const uint32_t cb = cand.y & 0xffu;
-                                    if (cb >= b) {
-                                        if (cb == b) {
-                                            c = na.x + t;
-                                            nc = cand;
-                                        }
-                                        break;
-                                    }
-                                }
-                            } else {
-                                uint32_t l0 = 0, l1 = nk;  // first child with byte >= b
-                                while (l0 < l1) {
-                                    const uint32_t mid = (l0 + l1) >> 1;
-                                    if ((__ldg(&sv.na[na.x + mid].meta) & 0xffu) < b)
-                                        l0 = mid + 1;
-                                    else
-                                        l1 = mid;
-                                }
-                                if (l0 < nk) {
-                                    const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + l0));
-                                    if ((cand.y & 0xffu) == b) {
-                                        c = na.x + l0;
-                                        nc = cand;
-                                    }
-                                }
-                            }
-                            v = c;
-                            na = nc;
-                            d++;
+                        const uint32_t mL = __shfl_sync(0xffffffffu, m1, L), exL = __shfl_sync(0xffffffffu, ex1, L);
+                        uint32_t k = 0;
+                        if (active) k = __fns(mL, 0, (int)(g - exL) + 1);
+                        const uint32_t rel = wrel + 16 * L + k;
+                        uint32_t ce = 0;
+                        if (CP) ce = cont_before(wbase + (active ? 16 * L + k + 1 : 0));
+                        if (active) {
+                            asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + (q1n + lane) * QE), "r"(rel) : "memory");
+                            if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + (q1n + lane) * QE + 4), "r"(ce) : "memory");
                         }
-                        if (best != kSieveNoNode) cnt = __ldg(&sv.nb[best].chain_cnt);
+                        q1n += min(tot1 - base, 32u);
+                        __syncwarp();
+                        while (q1n >= 32) round1();
                     }
-                    uint32_t total;
-                    const uint32_t exc = warp_excl_scan(cnt, lane, &total);
-                    if (total == 0) continue;
-                    // code points: continuation bytes between the counting origin of the match's haystack and its end
-                    uint32_t aux = 0;
-                    if (CP) {
-                        const uint32_t before = __reduce_add_sync(0xffffffffu, cp_lane);
-                        const int64_t e = (active ? p : wbase) + 1;
-                        const uint32_t upto_e = cont_upto(e);
-                        const bool inside = hs >= wbase;  // the haystack starts inside this window
-                        const uint32_t upto_hs = cont_upto(inside ? hs : wbase);
-                        aux = inside ? upto_e - upto_hs : before + upto_e - (h == h_prev ? cp_base : 0u);
-                    }
-                    unsigned long long rbase = 0;
-                    if (lane == 0) rbase = atomicAdd(out.raw_total, (unsigned long long)total);
-                    rbase = __shfl_sync(0xffffffffu, rbase, 0);
-                    if (cnt) {
-                        unsigned long long idx = rbase + exc;
-                        uint32_t seq = n_emitted + exc;
-                        const uint32_t end_rel = (uint32_t)(p + 1 - hs);
-                        for (uint32_t u = best; u != kSieveNoNode;) {
-                            const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(sv.nb + u));  // own_off, own_cnt, term_link, depth
-                            for (uint32_t t = 0; t < nb.y; t++, idx++, seq++) {
-                                if (idx < out.cap) {
-                                    const uint32_t pid = __ldg(sv.pids + nb.x + t);
-                                    reinterpret_cast<uint4 *>(out.raw)[idx] = make_uint4((uint32_t)h, pid, end_rel - nb.w, end_rel);
-                                    out.raw_seq[idx] = seq;
-                                    out.raw_unit[idx] = task;
-                                    if (CP) out.raw_aux[idx] = aux;
-                                }
-                            }
-                            u = nb.z;
-                        }
-                    }
-                    n_emitted += total;
+                    while (q2n >= 32) round2();
                 }
             }
-            if (CP) {
-                // the haystack holding the last byte of this window becomes "the haystack before the next window"
-                int64_t hs_end;
-                const int64_t h_end = hay_of(wend - 1, hs_end);
-                if (h_end != h_prev) {
-                    const uint32_t before = __reduce_add_sync(0xffffffffu, cp_lane);
-                    cp_base = before + cont_upto(max(hs_end, wbase));
-                    h_prev = h_end;
-                }
-                cp_lane += wc;
-            }
+            if (CP) cp_lane += wc;
             if (wbase >= wlast) break;
-            __syncwarp();  // every lane is done with the stash before its history is replaced
-            if (lane == 31) sts128(stash_s, cur);
+            // what is still queued from the window whose ring slot the next window will take has to go now
+            {
+                const uint32_t next_w = (wrel >> 9) + 1;
+                while (q1n && (lds32v(q1_s) >> 9) + R <= next_w) round1();
+                while (q2n && (lds32v(q2_s) >> 9) + R <= next_w) round2();
+            }
+            __syncwarp();  // every lane is done with the slot before its history is replaced
+            if (lane == 31) sts128(text_s(wrel + kWin) - 16, cur);
             carry_z = __shfl_sync(0xffffffffu, cur.z, 31);
             carry_w = __shfl_sync(0xffffffffu, cur.w, 31);
             cur = nx1;
             nx1 = nx2;
         }
+        while (q1n) round1();
+        while (q2n) round2();
         if (lane == 0) out.unit_counts[task] = n_emitted;
         if (CP) {
             const uint32_t all = __reduce_add_sync(0xffffffffu, cp_lane);
-            if (lane == 0) cont_tail[task] = all - cp_base;
+            if (lane == 0) task_cont[task] = all;
         }
         __syncwarp();
     }

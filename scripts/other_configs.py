@@ -20,13 +20,18 @@ def run(name, ac, data, offs, overlapping=False, steps=10):
     st = ac._ac.last_stats if hasattr(ac, "_ac") else {}
     print(f"{name}: {len(data)/1e6:.0f} MB, {total} matches, {ms:.3f} ms/step, {len(data)/ms/1e6:.1f} GB/s, stats {st}", flush=True)
 
-pats, data, offs = W.config3(n_patterns=10_000, n_lines=400_000)
-run("config3 (10k tokens, LeftmostLongest, 400k x 256 B)", BytesAhoCorasick(pats, MatchKind.LeftmostLongest), data, offs)
-pats, data, offs = W.config5(n_patterns=50_000, n_haystacks=25_000, hay_bytes=4096)
-run("config5 (50k patterns a-z, 25k x 4 KiB)", BytesAhoCorasick(pats), data, offs)
-pats, data = W.config4(n_patterns=100_000, hay_bytes=100_000_000)
-run("config4 (100k patterns, one 100 MB haystack, overlapping)", BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA), data,
-    np.array([0, len(data)], dtype=np.int64), overlapping=True, steps=5)
+only = [a for a in sys.argv[1:] if a in ("c3", "c4", "c5")]
+steps = 2 if "--short" in sys.argv else 10
+if not only or "c3" in only:
+    pats, data, offs = W.config3(n_patterns=10_000, n_lines=400_000)
+    run("config3 (10k tokens, LeftmostLongest, 400k x 256 B)", BytesAhoCorasick(pats, MatchKind.LeftmostLongest), data, offs, steps=steps)
+if not only or "c5" in only:
+    pats, data, offs = W.config5(n_patterns=50_000, n_haystacks=25_000, hay_bytes=4096)
+    run("config5 (50k patterns a-z, 25k x 4 KiB)", BytesAhoCorasick(pats), data, offs, steps=steps)
+if not only or "c4" in only:
+    pats, data = W.config4(n_patterns=100_000, hay_bytes=100_000_000)
+    run("config4 (100k patterns, one 100 MB haystack, overlapping)", BytesAhoCorasick(pats, implementation=Implementation.ContiguousNFA), data,
+        np.array([0, len(data)], dtype=np.int64), overlapping=True, steps=min(steps, 5))
 
 if "--large" in sys.argv:
     # one haystack above the 2 GiB window (BASELINE config 4's shape at 2.3 GB): two windows, checked against the oracle

@@ -49,7 +49,7 @@ class SieveImage:
         self.raw = buf
         f = struct.unpack_from(HDR_FMT, buf.tobytes()[: struct.calcsize(HDR_FMT)])
         (magic, self.W, self.last_level, self.n_probes, self.bloom_words, self.ht_mask, self.n_nodes, self.n_pids,
-         self.max_pat_len, self.min_pat_len, self.n_keys, self.n_entries, self.prim_words, _p0, _p1, _p2, o_bloom, o_ht, o_na, o_nb, o_pids, total) = f
+         self.max_pat_len, self.min_pat_len, self.n_keys, self.n_entries, self.prim_words, self.term_levels, _p1, _p2, o_bloom, o_ht, o_na, o_nb, o_pids, total) = f
         assert magic == 0x32424341 and total == n
         self.bloom = buf[o_bloom:o_bloom + 4 * self.bloom_words].view(np.uint32)
         self.ht = buf[o_ht:o_ht + 16 * (self.ht_mask + 1)].view(np.uint32).reshape(-1, 4)
@@ -113,7 +113,7 @@ class SieveImage:
             if d >= self.last_level and self.max_pat_len > self.last_level:
                 go = True
                 break
-            if self.has(xx ^ SALT_TERM):
+            if (self.term_levels >> d) & 1 and self.has(xx ^ SALT_TERM):
                 go = True
                 break
             if d >= self.last_level:
