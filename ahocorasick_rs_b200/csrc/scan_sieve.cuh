@@ -120,11 +120,13 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
 }
 
 // WC: 0 = W < 4 (the window word is shifted down), 1 = W == 4, 2 = W in 5..8 (two words)
+//
+// Positions inside a task are 32-bit offsets from the task's start (`rel`); the 64-bit stream position is t_lo + rel.
 template <bool CP, int WC>
 __global__ void __launch_bounds__(kSieveThreads, 1)
 sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_cont, uint32_t *hay_cont, unsigned int *task_counter) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t QE = CP ? 8u : 4u;  // queue entry: position (relative to the task start) [, continuation bytes before its end]
+    constexpr uint32_t QE = CP ? 8u : 4u;  // queue entry: position [, continuation bytes of the task before its end]
     const uint32_t bloom_s = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t bloom_bytes = sv.bloom_words * 4;
     const uint32_t bar_s = bloom_s + bloom_bytes;
@@ -170,6 +172,10 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         klo = W <= 4 ? lo >> sh_lo : lo;
         khi = W <= 4 ? 0u : hi >> sh_hi;
     };
+    auto q_store = [&](uint32_t q, uint32_t i, uint32_t rel, uint32_t ce) {
+        asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q + i * QE), "r"(rel) : "memory");
+        if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q + i * QE + 4), "r"(ce) : "memory");
+    };
 
     unsigned int claimed = 0;
     if (lane == 0) claimed = atomicAdd(task_counter, 1u);
@@ -178,64 +184,77 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         if ((int64_t)task >= P.n_tasks) break;
         if (lane == 0) claimed = atomicAdd(task_counter, 1u);  // the next one: its round trip overlaps this task
         const int64_t t_lo = P.origin + (int64_t)task * T;
-        const int64_t lo = max(t_lo, vlo), hi = min(t_lo + (int64_t)T, vhi);
-        if (lo >= hi) {
+        if (t_lo >= vhi || t_lo + (int64_t)T <= vlo) {
             if (lane == 0) {
                 out.unit_counts[task] = 0;
                 if (CP) task_cont[task] = 0;
             }
             continue;
         }
-        // positions (= index of a window's LAST byte) that can end a match: the window must lie inside the stream
-        const int64_t plo = max(lo, vlo + (int64_t)W - 1);
-        int64_t wbase = t_lo + ((lo - t_lo) & ~(int64_t)(kWin - 1));
-        const int64_t wlast = t_lo + ((hi - 1 - t_lo) & ~(int64_t)(kWin - 1));
+        // the task's part of the stream, [lo_r, hi_r) relative to t_lo; positions (= index of a window's LAST byte) from
+        // plo_r on can end a match: the W-byte window must lie inside the stream
+        const uint32_t lo_r = (uint32_t)max(vlo - t_lo, (int64_t)0), hi_r = (uint32_t)min(vhi - t_lo, (int64_t)T);
+        const uint32_t plo_r = (uint32_t)max((int64_t)lo_r, vlo + (int64_t)W - 1 - t_lo);
+        const uint8_t *tptr = B.bytes + t_lo;  // (may point before the buffer: only [lo_r, hi_r) is ever dereferenced)
+        const uint32_t wfirst = lo_r & ~(kWin - 1), wlast = (hi_r - 1) & ~(kWin - 1);
+        auto load16 = [&](uint32_t rel) -> uint4 {  // 16 bytes at rel (may be "negative": the history before the task)
+            const int64_t q = t_lo + (int64_t)(int32_t)rel;
+            return load_chunk(B.bytes, q, vlo, vhi);
+        };
 
-        // ---- haystack bookkeeping: lane l caches offsets[hb + l] (stream positions fit 32 bits: one call scans < 4 GiB) ----
+        // ---- haystack bookkeeping: lane l caches the start of haystack hb + l, relative to the task (saturated) ----
         int64_t hb;
         {
+            const int64_t lo = t_lo + lo_r;
             int64_t h = P.avg_len ? (int64_t)((uint64_t)(lo - stream_lo) / P.avg_len) : 0;
             if (h >= B.n_haystacks) h = B.n_haystacks - 1;
             if (!(__ldg(B.offsets + h) <= lo && lo < __ldg(B.offsets + h + 1))) h = find_haystack(B, lo);
             hb = h;
         }
-        auto load_offc = [&](int64_t base) -> uint32_t {
+        auto load_offc = [&](int64_t base) -> int32_t {
             const int64_t idx = base + lane;
-            return idx <= B.n_haystacks ? (uint32_t)__ldg(B.offsets + idx) : 0xffffffffu;
+            if (idx > B.n_haystacks) return 0x7fffffff;
+            const int64_t d = __ldg(B.offsets + idx) - t_lo;
+            return (int32_t)max(min(d, (int64_t)0x7ffffffe), (int64_t)-0x7fffffff);
         };
-        uint32_t offc = load_offc(hb);
-        // Haystack containing byte p, and its start.  The shuffles are executed by the whole warp (p may differ per lane).
-        // Positions before the cached range (queued in an earlier window) walk back from it; a window with more than
-        // 31 haystack starts (haystacks of a few bytes) falls back to a search.
-        auto hay_of = [&](int64_t p, int64_t &hs) -> int64_t {
+        int32_t offc = load_offc(hb);
+        int32_t next_start = __shfl_sync(0xffffffffu, offc, 1);  // start of haystack hb + 1
+        // Haystack containing the byte at rel, and its start (relative).  The shuffles are executed by the whole warp (rel
+        // may differ per lane).  Positions before the cached range (queued in an earlier window) walk back from it; a
+        // window with more than 31 haystack starts (haystacks of a few bytes) falls back to a search.
+        auto hay_of = [&](uint32_t rel, int32_t &hs) -> int64_t {
+            const int32_t p = (int32_t)rel;
             uint32_t l = 0;
 #pragma unroll
             for (int step = 16; step >= 1; step >>= 1) {
                 const uint32_t c = l + step;
-                const uint32_t v = __shfl_sync(0xffffffffu, offc, c & 31);
-                if (c < 32 && (int64_t)v <= p) l = c;
+                const int32_t v = __shfl_sync(0xffffffffu, offc, c & 31);
+                if (c < 32 && v <= p) l = c;
             }
-            hs = (int64_t)__shfl_sync(0xffffffffu, offc, l);
+            hs = __shfl_sync(0xffffffffu, offc, l);
             int64_t h = hb + l;
             if (hs > p) {
                 // before the cache: the haystack is a few entries back
+                const int64_t pa = t_lo + p;
                 int64_t step = 1, below = hb;
-                while (below > 0 && __ldg(B.offsets + below) > p) {
+                while (below > 0 && __ldg(B.offsets + below) > pa) {
                     below = max(below - step, (int64_t)0);
                     step <<= 1;
                 }
                 h = below;
-                while (h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= p) h++;  // last haystack that starts at or before p
-                hs = __ldg(B.offsets + h);
-            } else if (l == 31 && h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= p) {
-                h = find_haystack(B, p);
-                hs = __ldg(B.offsets + h);
+                while (h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= pa) h++;  // last haystack that starts at or before p
+                hs = (int32_t)max(__ldg(B.offsets + h) - t_lo, (int64_t)-0x7fffffff);
+            } else if (l == 31 && h + 1 < B.n_haystacks && __ldg(B.offsets + h + 1) <= t_lo + p) {
+                h = find_haystack(B, t_lo + p);
+                hs = (int32_t)max(__ldg(B.offsets + h) - t_lo, (int64_t)-0x7fffffff);
             }
             return h;
         };
 
         uint32_t n_emitted = 0, q1n = 0, q2n = 0;
-        uint32_t cp_lane = 0;  // code points: continuation bytes seen by this lane in earlier windows of the task
+        uint32_t q1_head = 0, q2_head = 0;  // window index of each queue's first entry (valid while the queue is not empty)
+        uint32_t cp_lane = 0;               // code points: continuation bytes seen by this lane in earlier windows of the task
+        uint32_t wrel = wfirst;
 
         // ---- stage 2: exact verification of the first (up to) 32 positions of the second queue ----
         auto round2 = [&]() {
@@ -246,11 +265,10 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 rel = lds32v(q2_s + lane * QE);
                 if (CP) aux = lds32v(q2_s + lane * QE + 4);
             }
-            const int64_t p = t_lo + rel;  // last byte of the candidate; the match would end at e = p + 1
-            int64_t hs;
-            const int64_t h = hay_of(active ? p : max(wbase, lo), hs);
+            int32_t hs;
+            const int64_t h = hay_of(active ? rel : max(wrel, lo_r), hs);
             uint32_t best = kSieveNoNode, cnt = 0;
-            if (active && p - (int64_t)(W - 1) >= hs) {
+            if (active && (int32_t)rel - (int32_t)(W - 1) >= hs) {
                 uint32_t klo, khi;
                 stash_key(rel, klo, khi);
                 const uint32_t x = klo + khi * kMixHi;
@@ -265,15 +283,15 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                     }
                     s = (s + 1) & (sv.ht_size - 1);
                 }
-                // walk towards the pattern start: node v = the d bytes before e
+                // walk towards the pattern start: node v = the d bytes that end at rel
                 uint32_t d = W;
                 uint2 na = make_uint2(0, 0);
                 if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
                 while (v != kSieveNoNode) {
                     if (na.y & kNodeTerminal) best = v;
                     const uint32_t nk = (na.y >> 8) & 0x1ffu;
-                    if (nk == 0 || p - (int64_t)d < hs) break;  // no longer pattern, or it would start before the haystack
-                    const uint32_t b = __ldg(B.bytes + (p - (int64_t)d));
+                    if (nk == 0 || (int32_t)rel - (int32_t)d < hs) break;  // no longer pattern, or it would start before the haystack
+                    const uint32_t b = __ldg(tptr + ((int64_t)(int32_t)rel - (int64_t)d));
                     uint32_t c = kSieveNoNode;
                     uint2 nc = make_uint2(0, 0);
                     if (nk <= 8) {
@@ -311,16 +329,17 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 }
                 if (best != kSieveNoNode) cnt = __ldg(&sv.nb[best].chain_cnt);
             }
-            uint32_t total;
-            const uint32_t exc = warp_excl_scan(cnt, lane, &total);
-            if (total) {
+            const uint32_t hits = __ballot_sync(0xffffffffu, cnt != 0);
+            if (hits) {
+                uint32_t total;
+                const uint32_t exc = warp_excl_scan(cnt, lane, &total);
                 unsigned long long rbase = 0;
                 if (lane == 0) rbase = atomicAdd(out.raw_total, (unsigned long long)total);
                 rbase = __shfl_sync(0xffffffffu, rbase, 0);
                 if (cnt) {
                     unsigned long long idx = rbase + exc;
                     uint32_t seq = n_emitted + exc;
-                    const uint32_t end_rel = (uint32_t)(p + 1 - hs);
+                    const uint32_t end_rel = (uint32_t)((int32_t)rel + 1 - hs);
                     for (uint32_t u = best; u != kSieveNoNode;) {
                         const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(sv.nb + u));  // own_off, own_cnt, term_link, depth
                         for (uint32_t t = 0; t < nb.y; t++, idx++, seq++) {
@@ -345,11 +364,9 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 if (CP) keep.y = lds32v(q2_s + (32 + lane) * QE + 4);
             }
             __syncwarp();
-            if (mv) {
-                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + lane * QE), "r"(keep.x) : "memory");
-                if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + lane * QE + 4), "r"(keep.y) : "memory");
-            }
+            if (mv) q_store(q2_s, lane, keep.x, keep.y);
             q2n -= n;
+            q2_head = __shfl_sync(0xffffffffu, keep.x, 0) >> 9;
             __syncwarp();
         };
 
@@ -387,12 +404,11 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 }
             }
             const uint32_t surv = __ballot_sync(0xffffffffu, go);
-            if (go) {
-                const uint32_t at = q2n + __popc(surv & ((1u << lane) - 1u));
-                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + at * QE), "r"(rel) : "memory");
-                if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2_s + at * QE + 4), "r"(aux) : "memory");
+            if (surv) {
+                if (go) q_store(q2_s, q2n + __popc(surv & ((1u << lane) - 1u)), rel, aux);
+                if (q2n == 0) q2_head = __shfl_sync(0xffffffffu, rel, __ffs(surv) - 1) >> 9;
+                q2n += __popc(surv);
             }
-            q2n += __popc(surv);
             // pop the round
             uint2 keep = make_uint2(0, 0);
             const bool mv = 32 + lane < q1n;
@@ -401,27 +417,31 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 if (CP) keep.y = lds32v(q1_s + (32 + lane) * QE + 4);
             }
             __syncwarp();
-            if (mv) {
-                asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + lane * QE), "r"(keep.x) : "memory");
-                if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + lane * QE + 4), "r"(keep.y) : "memory");
-            }
+            if (mv) q_store(q1_s, lane, keep.x, keep.y);
             q1n -= n;
+            q1_head = __shfl_sync(0xffffffffu, keep.x, 0) >> 9;
             __syncwarp();
         };
 
         uint32_t carry_z = 0, carry_w = 0;
         {
-            const uint4 c = load_chunk(B.bytes, wbase - 16, vlo, vhi);
+            const uint4 c = load16(wrel - 16);
             carry_z = c.z;
             carry_w = c.w;
-            if (lane == 0) sts128(text_s((uint32_t)(wbase - t_lo)) - 16, c);
+            if (lane == 0) sts128(text_s(wrel) - 16, c);
         }
-        uint4 cur = load_chunk(B.bytes, wbase + 16 * lane, vlo, vhi);
+        uint4 cur = load16(wrel + 16 * lane);
         uint4 nx1 = make_uint4(0, 0, 0, 0), nx2 = make_uint4(0, 0, 0, 0);
-        if (wbase + kWin <= wlast) nx1 = load_chunk(B.bytes, wbase + kWin + 16 * lane, vlo, vhi);
+        if (wrel + kWin <= wlast) nx1 = load16(wrel + kWin + 16 * lane);
 
-        for (;; wbase += kWin) {
-            if (wbase + 2 * (int64_t)kWin <= wlast) nx2 = load_chunk(B.bytes, wbase + 2 * kWin + 16 * lane, vlo, vhi);
+        for (;; wrel += kWin) {
+            if (wrel + 2 * kWin <= wlast) {
+                // two windows ahead: whole windows inside the stream (all but a task's edges) take the direct load
+                if (wrel + 2 * kWin >= lo_r && wrel + 3 * kWin <= hi_r)
+                    nx2 = __ldg(reinterpret_cast<const uint4 *>(tptr + (wrel + 2 * kWin + 16 * lane)));
+                else
+                    nx2 = load16(wrel + 2 * kWin + 16 * lane);
+            }
             // ---- fast path: first filter probe for the 16 positions of this lane ----
             uint32_t pz = __shfl_up_sync(0xffffffffu, cur.z, 1), pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
             if (lane == 0) {
@@ -448,28 +468,29 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 acc = __funnelshift_r(acc, shf_r_wrap(word, 0u, p), 1);  // bit (p & 31) of the word -> top of acc
             }
             uint32_t m1 = acc >> 16;
-            // positions outside [plo, hi) cannot end a match (first and last window of the task only)
-            const int64_t q = wbase + 16 * lane;
-            if (wbase < plo || wbase + (int64_t)kWin > hi) {
-                const int from = (int)min(max(plo - q, (int64_t)0), (int64_t)16), to = (int)min(max(hi - q, (int64_t)0), (int64_t)16);
+            // positions outside [plo_r, hi_r) cannot end a match (first and last window of the task only)
+            if (wrel < plo_r || wrel + kWin > hi_r) {
+                const int32_t q = (int32_t)(wrel + 16 * lane);
+                const int from = min(max((int32_t)plo_r - q, 0), 16), to = min(max((int32_t)hi_r - q, 0), 16);
                 m1 &= ((1u << to) - 1u) & ~((1u << from) - 1u);
             }
-            const uint32_t wrel = (uint32_t)(wbase - t_lo);  // this window, relative to the task
-            const int64_t wend = min(wbase + (int64_t)kWin, hi);  // one past the last stream byte of this window
-            // does the cached offset range still start at the haystack that holds this window's first byte?
-            if ((int64_t)__shfl_sync(0xffffffffu, offc, 1) <= wbase) {
-                const int64_t first = max(wbase, lo);
-                const uint32_t ahead = __popc(__ballot_sync(0xffffffffu, (int64_t)offc <= first));
-                hb = ahead == 32 ? find_haystack(B, first) : hb + ahead - 1;
+            const uint32_t wend = min(wrel + kWin, hi_r);  // one past the last stream byte of this window
+            // does the cached range still start at the haystack that holds this window's first byte?
+            if (next_start <= (int32_t)wrel) {
+                const int32_t first = (int32_t)max(wrel, lo_r);
+                const uint32_t ahead = __popc(__ballot_sync(0xffffffffu, offc <= first));
+                hb = ahead == 32 ? find_haystack(B, t_lo + first) : hb + ahead - 1;
                 offc = load_offc(hb);
+                next_start = __shfl_sync(0xffffffffu, offc, 1);
             }
             uint32_t wc = 0;  // code points: continuation bytes in this lane's chunk
-            bool starts_inside = false;
+            bool starts_inside = false, wany = false;
             if (CP) {
-                if ((cur.x | cur.y | cur.z | cur.w) & 0x80808080u) wc = cont_bytes(cur.x) + cont_bytes(cur.y) + cont_bytes(cur.z) + cont_bytes(cur.w);
+                const bool high = ((cur.x | cur.y | cur.z | cur.w) & 0x80808080u) != 0;
+                if (high) wc = cont_bytes(cur.x) + cont_bytes(cur.y) + cont_bytes(cur.z) + cont_bytes(cur.w);
+                wany = __any_sync(0xffffffffu, high);
                 // haystacks that START in this window record how many continuation bytes the task has seen before them
-                const int64_t o0 = (int64_t)__shfl_sync(0xffffffffu, offc, 0), o1 = (int64_t)__shfl_sync(0xffffffffu, offc, 1);
-                starts_inside = o0 >= max(wbase, lo) || o1 < wend;
+                starts_inside = next_start < (int32_t)wend || __shfl_sync(0xffffffffu, offc, 0) >= (int32_t)max(wrel, lo_r);
             }
             const bool any = __any_sync(0xffffffffu, m1 != 0);
             if (any || starts_inside) {
@@ -477,67 +498,97 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 __syncwarp();
                 uint32_t exw = 0, wtot = 0, before = 0;
                 if (CP) {
-                    exw = warp_excl_scan(wc, lane, &wtot);
+                    if (wany) exw = warp_excl_scan(wc, lane, &wtot);
                     before = __reduce_add_sync(0xffffffffu, cp_lane);
                 }
-                // continuation bytes in [lo, pos) for pos in [wbase, wbase + 512]; executed by the whole warp
-                auto cont_before = [&](int64_t pos) -> uint32_t {
-                    const uint32_t rl = (uint32_t)(pos - wbase);
-                    const uint32_t L = min(rl >> 4, 31u);
-                    const uint32_t ex = __shfl_sync(0xffffffffu, exw, L);
-                    if (wtot == 0) return before;  // (an ASCII window: nothing to add)
-                    return before + ex + cont_prefix(text_s(wrel) + 16 * L, rl - 16 * L);
-                };
                 if (CP && starts_inside) {
+                    // continuation bytes in [lo_r, pos) for pos in [wrel, wrel + 512]; executed by the whole warp
+                    auto cont_before = [&](uint32_t pos) -> uint32_t {
+                        const uint32_t rl = pos - wrel;
+                        const uint32_t L = min(rl >> 4, 31u);
+                        const uint32_t ex = __shfl_sync(0xffffffffu, exw, L);
+                        if (wtot == 0) return before;  // (an ASCII window: nothing to add)
+                        return before + ex + cont_prefix(text_s(wrel) + 16 * L, rl - 16 * L);
+                    };
                     for (;;) {
-                        const int64_t s = (int64_t)offc;
-                        const bool mine = s >= max(wbase, lo) && s < wend && hb + lane < B.n_haystacks;
-                        const uint32_t c = cont_before(mine ? s : wbase);
+                        const bool mine = offc >= (int32_t)max(wrel, lo_r) && offc < (int32_t)wend && hb + lane < B.n_haystacks;
+                        const uint32_t c = cont_before(mine ? (uint32_t)offc : wrel);
                         if (mine) hay_cont[hb + lane] = c;
                         // more than 32 starts in one window: move the cache on and repeat
-                        if ((int64_t)__shfl_sync(0xffffffffu, offc, 31) >= wend || hb + 31 >= B.n_haystacks) break;
+                        if (__shfl_sync(0xffffffffu, offc, 31) >= (int32_t)wend || hb + 31 >= B.n_haystacks) break;
                         hb += 31;
                         offc = load_offc(hb);
+                        next_start = __shfl_sync(0xffffffffu, offc, 1);
                     }
                 }
                 if (any) {
-                    // ---- queue this window's survivors, in stream order (lane i takes the (base + i)-th of them) ----
+                    // ---- queue this window's survivors, in stream order: a lane's go behind those of the lanes before it ----
                     uint32_t tot1;
                     const uint32_t ex1 = warp_excl_scan(__popc(m1), lane, &tot1);
-                    for (uint32_t base = 0; base < tot1; base += 32) {
-                        const uint32_t g = base + lane;
-                        const bool active = g < tot1;
-                        uint32_t L = 0;
+                    if (q1n + tot1 <= kQueueCap) {
+                        uint32_t at = q1n + ex1;
+                        for (uint32_t m = m1; m; m &= m - 1) {
+                            const uint32_t k = __ffs(m) - 1;
+                            uint32_t ce = 0;
+                            if (CP) {
+                                ce = before;
+                                if (wtot) {
+                                    // continuation bytes of this window before the candidate's end: the lanes before, and the own bytes 0..k
+                                    const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
+                                    uint32_t own = 0;
 #pragma unroll
-                        for (int step = 16; step >= 1; step >>= 1) {
-                            const uint32_t c = L + step;
-                            const uint32_t v = __shfl_sync(0xffffffffu, ex1, c & 31);
-                            if (c < 32 && v <= g) L = c;
+                                    for (int w = 0; w < 4; w++) {
+                                        const int left = (int)k + 1 - 4 * w;
+                                        const uint32_t mask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u));
+                                        own += __popc(w4[w] & ~(w4[w] << 1) & 0x80808080u & mask);
+                                    }
+                                    ce += exw + own;
+                                }
+                            }
+                            q_store(q1_s, at++, wrel + 16 * lane + k, ce);
                         }
-                        const uint32_t mL = __shfl_sync(0xffffffffu, m1, L), exL = __shfl_sync(0xffffffffu, ex1, L);
-                        uint32_t k = 0;
-                        if (active) k = __fns(mL, 0, (int)(g - exL) + 1);
-                        const uint32_t rel = wrel + 16 * L + k;
-                        uint32_t ce = 0;
-                        if (CP) ce = cont_before(wbase + (active ? 16 * L + k + 1 : 0));
-                        if (active) {
-                            asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + (q1n + lane) * QE), "r"(rel) : "memory");
-                            if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + (q1n + lane) * QE + 4), "r"(ce) : "memory");
-                        }
-                        q1n += min(tot1 - base, 32u);
+                        if (q1n == 0) q1_head = wrel >> 9;
+                        q1n += tot1;
                         __syncwarp();
                         while (q1n >= 32) round1();
+                    } else {
+                        // a window with more survivors than the queue takes at once: 32 at a time (lane i takes the (base + i)-th)
+                        for (uint32_t base = 0; base < tot1; base += 32) {
+                            const uint32_t g = base + lane;
+                            const bool active = g < tot1;
+                            uint32_t L = 0;
+#pragma unroll
+                            for (int step = 16; step >= 1; step >>= 1) {
+                                const uint32_t c = L + step;
+                                const uint32_t v = __shfl_sync(0xffffffffu, ex1, c & 31);
+                                if (c < 32 && v <= g) L = c;
+                            }
+                            const uint32_t mL = __shfl_sync(0xffffffffu, m1, L), exL = __shfl_sync(0xffffffffu, ex1, L);
+                            uint32_t k = 0;
+                            if (active) k = __fns(mL, 0, (int)(g - exL) + 1);
+                            uint32_t ce = 0;
+                            if (CP) {
+                                const uint32_t ex = __shfl_sync(0xffffffffu, exw, L);
+                                ce = before;
+                                if (wtot) ce += ex + cont_prefix(text_s(wrel) + 16 * L, k + 1);
+                            }
+                            if (active) q_store(q1_s, q1n + lane, wrel + 16 * L + k, ce);
+                            if (q1n == 0) q1_head = wrel >> 9;
+                            q1n += min(tot1 - base, 32u);
+                            __syncwarp();
+                            while (q1n >= 32) round1();
+                        }
                     }
                     while (q2n >= 32) round2();
                 }
             }
             if (CP) cp_lane += wc;
-            if (wbase >= wlast) break;
+            if (wrel >= wlast) break;
             // what is still queued from the window whose ring slot the next window will take has to go now
             {
                 const uint32_t next_w = (wrel >> 9) + 1;
-                while (q1n && (lds32v(q1_s) >> 9) + R <= next_w) round1();
-                while (q2n && (lds32v(q2_s) >> 9) + R <= next_w) round2();
+                while (q1n && q1_head + R <= next_w) round1();
+                while (q2n && q2_head + R <= next_w) round2();
             }
             __syncwarp();  // every lane is done with the slot before its history is replaced
             if (lane == 31) sts128(text_s(wrel + kWin) - 16, cur);

@@ -127,6 +127,7 @@ class _Automaton:
         self._ws = {}          # device index -> dict of tensors
         self.last_stats = {}
         self._lock = threading.Lock()
+        self._host_lock = threading.RLock()   # host-buffer calls: staging buffer + workspaces until the results are on the host
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -251,10 +252,11 @@ class _Automaton:
             raise RuntimeError(_capi.last_error())
         return plan
 
-    def _workspace(self, device, plan, n_haystacks: int, capacity: int):
+    def _workspace(self, device, plan, n_haystacks: int, capacity: int, slot: int = 0):
         torch = _torch()
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        ws = self._ws.get(idx)
+        key = (idx, slot)   # (the host pipeline alternates between two workspaces)
+        ws = self._ws.get(key)
         need = (ws is None or ws["n_units"] < plan.n_units or ws["n_segments"] < plan.n_segments or
                 ws["scratch"].numel() < plan.scratch_words or ws["n_haystacks"] < n_haystacks or ws["capacity"] < capacity)
         if need:
@@ -278,7 +280,7 @@ class _Automaton:
                 "out": torch.empty((cap, 4), dtype=torch.int32, device=dev),
                 "match_offsets": torch.empty(n_hay + 1, dtype=torch.int64, device=dev),
             }
-            self._ws[idx] = ws
+            self._ws[key] = ws
         return ws
 
     def _ws_struct(self, ws):
@@ -305,14 +307,18 @@ class _Automaton:
 
     # ---- scans ------------------------------------------------------------------
     def scan_device(self, data, offsets, overlapping=False, codepoints=False, capacity: Optional[int] = None,
-                    sync: bool = True):
+                    sync: bool = True, ws_slot: int = 0):
         """Scan a device-resident batch.  data: uint8 CUDA tensor, offsets: int64
         CUDA tensor (n+1).  One haystack of any size is simply n = 1.  Returns
         (matches, match_offsets, total): matches is an int32 CUDA tensor
         (total, 4) = (haystack, pattern, start, end) in the reference's order,
         match_offsets (n+1) brackets each haystack's rows.  With sync=False the
         call returns right after enqueueing (total is the 8-entry device status
-        tensor and matches the whole capacity-sized buffer)."""
+        tensor and matches the whole capacity-sized buffer).
+
+        The returned tensors are VIEWS of this automaton's workspace `ws_slot` on the
+        device: they are valid until the next scan that uses the same slot (copy them,
+        or use scan_host / the find_* methods, when several threads share one automaton)."""
         torch = _require_cuda()
         self.check_overlapping(overlapping)
         dev = data.device
@@ -336,7 +342,7 @@ class _Automaton:
                 hot = self.hot(dev, data, offsets, overlapping)
             plan = self._plan(data, n)
             while True:
-                ws = self._workspace(dev, plan, n, cap)
+                ws = self._workspace(dev, plan, n, cap, ws_slot)
                 st = self._ws_struct(ws)
                 rc = self._L.acb_scan_batch(self._h, img.data_ptr(),
                                             hot["tensor"].data_ptr() if hot else None, C.byref(hot["rows"]) if hot else None,
@@ -423,8 +429,115 @@ class _Automaton:
         parts = scan_in_windows(scan_window, hay, self.WINDOW_BYTES, max(self.max_pattern_len - 1, 0), codepoints)
         return torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
 
+    # ---- host-resident input (the reference's situation: src/lib.rs:229-249, 422-434 take host str / buffers) ----
+    HOST_CHUNK_BYTES = 64 << 20    # pipeline granularity: copy of chunk i+1 overlaps the scan of chunk i
+    _staging = None                # grow-only pinned staging buffer for inputs that are not pinned already
+
+    def _pinned(self, nbytes: int):
+        torch = _torch()
+        st = self._staging
+        if st is None or st.numel() < nbytes:
+            st = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8, pin_memory=True)
+            self._staging = st
+        return st
+
+    def scan_host(self, data, offsets, overlapping: bool = False, codepoints: bool = False, chunk_bytes: Optional[int] = None):
+        """Scan a batch that lives in HOST memory: data = 1-D uint8 (numpy array or CPU torch tensor; pinned memory
+        makes the copies asynchronous), offsets = int64 (n + 1).  Returns host numpy arrays
+        (matches (k, 4) uint32 -- int64 when a window path was needed --, match_offsets (n + 1) int64).
+
+        Large inputs are cut into runs of whole haystacks of about `chunk_bytes`: the host->device copy of run i+1
+        (copy stream, second device buffer) overlaps the scan of run i, whose results are copied back while run i+1
+        is scanned (two workspaces).  The whole call holds the automaton's lock, so threads sharing one automaton
+        are serialised here instead of corrupting each other's workspace."""
+        torch = _require_cuda()
+        self.check_overlapping(overlapping)
+        if isinstance(data, np.ndarray):
+            hdata = torch.from_numpy(data) if data.flags.writeable else torch.from_numpy(data.copy())
+        else:
+            hdata = data
+        offs = offsets.numpy() if hasattr(offsets, "numpy") else np.asarray(offsets)
+        offs = np.ascontiguousarray(offs, dtype=np.int64)
+        n = len(offs) - 1
+        total_bytes = int(offs[-1] - offs[0]) if n > 0 else 0
+        dev = torch.device("cuda", torch.cuda.current_device())
+        chunk = int(chunk_bytes or self.HOST_CHUNK_BYTES)
+        with self._host_lock:
+            if n <= 0 or total_bytes <= chunk or int(np.max(np.diff(offs))) > self.WINDOW_BYTES:
+                # one shot (small input), or the oversized-haystack window path
+                lo, hi = (int(offs[0]), int(offs[-1])) if n > 0 else (0, 0)
+                d_data = hdata[lo:hi].to(dev, non_blocking=True)
+                d_offs = torch.from_numpy(offs - lo).to(dev, non_blocking=True)
+                m, moffs, _ = self.scan_device(d_data, d_offs, overlapping, codepoints)
+                m = m.cpu().numpy()
+                return (m.view(np.uint32) if m.dtype == np.int32 else m), moffs.cpu().numpy().astype(np.int64)
+            # runs of whole haystacks
+            cuts = [0]
+            while cuts[-1] < n:
+                h0 = cuts[-1]
+                h1 = int(np.searchsorted(offs, offs[h0] + chunk, side="right")) - 1
+                cuts.append(min(max(h1, h0 + 1), n))
+            runs = list(zip(cuts[:-1], cuts[1:]))
+            max_bytes = max(int(offs[b] - offs[a]) for a, b in runs)
+            max_hay = max(b - a for a, b in runs)
+            dbuf = [torch.empty(max_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+            doff = [torch.empty(max_hay + 1, dtype=torch.int64, device=dev) for _ in range(2)]
+            hoff = [torch.empty(max_hay + 1, dtype=torch.int64, pin_memory=True) for _ in range(2)]
+            main = torch.cuda.current_stream(dev)
+            copier = torch.cuda.Stream(device=dev)
+            scanned = [None, None]
+            parts, counts = [], np.zeros(n, dtype=np.int64)
+            cap = max(4096, 2 * max_hay)
+
+            def collect(job):
+                slot, a, b, nbytes, out, mo, tot = job
+                t = tot.tolist()            # waits for that run's scan only
+                total, complete, raw_total = t[0], t[1], t[4]
+                if not (complete or (total == 0 and raw_total == 0)):
+                    # rare: the run had more matches than room; redo it with what it needs
+                    m, mo2, total = self.scan_device(dbuf[slot][:nbytes], doff[slot][: b - a + 1], overlapping, codepoints,
+                                                     capacity=max(total, raw_total) + max(total, raw_total) // 8 + 16, ws_slot=slot)
+                    out, mo = m, mo2
+                part = out[:total].cpu().numpy().view(np.uint32).copy()
+                part[:, 0] += a
+                parts.append(part)
+                counts[a:b] = np.diff(mo[: b - a + 1].cpu().numpy())
+
+            pending = None
+            for i, (a, b) in enumerate(runs):
+                slot = i & 1
+                nbytes = int(offs[b] - offs[a])
+                with torch.cuda.stream(copier):
+                    if scanned[slot] is not None:
+                        copier.wait_event(scanned[slot])   # the scan that read this device buffer two runs ago
+                    dbuf[slot][:nbytes].copy_(hdata[int(offs[a]):int(offs[b])], non_blocking=True)
+                    hoff[slot][: b - a + 1].copy_(torch.from_numpy(offs[a:b + 1] - offs[a]))
+                    doff[slot][: b - a + 1].copy_(hoff[slot][: b - a + 1], non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(copier)
+                main.wait_event(copied)
+                if pending is not None and pending[0] == slot:
+                    collect(pending)        # (never: slots alternate) keeps the workspace of this slot free
+                    pending = None
+                out, mo, tot = self.scan_device(dbuf[slot][:nbytes], doff[slot][: b - a + 1], overlapping, codepoints,
+                                                capacity=cap, sync=False, ws_slot=slot)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                scanned[slot] = ev
+                job = (slot, a, b, nbytes, out, mo, tot)
+                if pending is not None:
+                    collect(pending)        # D2H of the previous run while this one is being scanned
+                pending = job
+            collect(pending)
+            m = np.concatenate(parts, axis=0) if parts else np.zeros((0, 4), dtype=np.uint32)
+            mo = np.zeros(n + 1, dtype=np.int64)
+            np.cumsum(counts, out=mo[1:])
+            return m, mo
+
     def scan_host_batch(self, chunks: Sequence[bytes], overlapping: bool, codepoints: bool):
-        """Host buffers in, host numpy out: (matches uint32 (k,4), match_offsets int64 (n+1))."""
+        """Host buffers (bytes-like objects, one per haystack) in, host numpy out: (matches uint32 (k,4),
+        match_offsets int64 (n+1)).  The haystacks are gathered into this automaton's pinned staging buffer
+        (for a single haystack: one copy straight out of the caller's buffer), then scan_host takes over."""
         torch = _require_cuda()
         self.check_overlapping(overlapping)
         n = len(chunks)
@@ -432,18 +545,14 @@ class _Automaton:
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
         total_bytes = int(offs[-1])
-        dev = torch.device("cuda", torch.cuda.current_device())
-        host = torch.empty(max(total_bytes, 1), dtype=torch.uint8, pin_memory=True)
-        hv = host.numpy()
-        if n == 1:
-            hv[:total_bytes] = np.frombuffer(chunks[0], dtype=np.uint8)
-        elif total_bytes:
-            hv[:total_bytes] = np.frombuffer(b"".join(chunks), dtype=np.uint8)  # one C-speed concatenation, one copy into pinned memory
-        d_data = host.to(dev, non_blocking=True)[:total_bytes]
-        d_offs = torch.from_numpy(offs).to(dev, non_blocking=True)
-        m, moffs, _ = self.scan_device(d_data, d_offs, overlapping, codepoints)
-        m = m.cpu().numpy()
-        return (m.view(np.uint32) if m.dtype == np.int32 else m), moffs.cpu().numpy()
+        with self._host_lock:
+            host = self._pinned(total_bytes)
+            hv = host.numpy()
+            if n == 1:
+                hv[:total_bytes] = np.frombuffer(chunks[0], dtype=np.uint8)
+            elif total_bytes:
+                hv[:total_bytes] = np.frombuffer(b"".join(chunks), dtype=np.uint8)  # one C-speed concatenation, one copy into pinned memory
+            return self.scan_host(host[:total_bytes], offs, overlapping, codepoints)
 
 
 def _as_buffer_bytes(obj) -> bytes:
@@ -460,7 +569,9 @@ def _as_buffer_bytes(obj) -> bytes:
         raise TypeError("Must be a contiguous sequence of bytes")
     if mv.itemsize != 1 or mv.format not in ("B", "b", "c"):
         raise BufferError("buffer contents are not compatible with u8")
-    return mv.tobytes() if not isinstance(obj, bytes) else obj
+    # zero-copy like the reference's PyBufferBytes (src/lib.rs:304-340): the caller's memory is read in place (one copy,
+    # into the pinned staging buffer the H2D transfer starts from); as there, the caller must not mutate it meanwhile
+    return obj if isinstance(obj, bytes) else (mv if mv.format == "B" else mv.cast("B"))
 
 
 def _tuples(m: np.ndarray):
