@@ -6,8 +6,9 @@
 //   [ per warp: R x (16 B history | 512 B window) | 16 B pad ]   the "stash": a ring of the last R windows of text the
 //        warp looked at, for the few positions that survive the first probe (their hash is recomputed from here, the
 //        on-chip walk reads older bytes from here); a window is written only when it has survivors
-//   [ per warp: two queues of 64 positions ]   survivors of the first probe waiting for stage 1, survivors of stage 1
-//        waiting for stage 2: the later stages run 32 positions at a time (one per lane) whatever window they came from
+//   [ per warp: two queues of 64 entries ]   survivors of the first probe waiting for stage 1 (positions: their text is
+//        in the ring), survivors of stage 1 waiting for stage 2 (position + key: they need nothing from the ring): the
+//        later stages run 32 positions at a time (one per lane) whatever window they came from
 //
 // Work: the byte stream is cut into TASKS of task_bytes (a multiple of 512) on a grid anchored at a 512-byte aligned
 // address; warps claim tasks from an atomic counter and walk them in 512-byte WINDOWS: lane l holds bytes
@@ -36,14 +37,16 @@
 
 namespace acb {
 
-constexpr int kSieveWarps = 32;
+constexpr int kSieveWarps = 24;   // 768 threads: 85 registers per thread (with 32 warps the window loop rematerialised half its state)
 constexpr int kSieveThreads = kSieveWarps * 32;
 constexpr uint32_t kWin = 512;                       // bytes per warp window
-constexpr uint32_t kSlotBytes = 16 + kWin;           // one ring slot: 16 bytes of history, then the window
+constexpr uint32_t kSlotText = 16 + kWin;            // one ring slot: 16 bytes of history, then the window,
+constexpr uint32_t kSlotBytes = kSlotText + 48;      // then (code points) continuation bytes per 16-byte chunk (32 x u8) and before the window (u32)
 constexpr uint32_t kQueueCap = 64;                   // positions per queue (a round takes 32; at most 32 arrive at a time)
 constexpr uint32_t kRingMax = 8;
-// per warp: ring | pad | two queues (entries: 4 bytes, or 8 with the code point count)
-__host__ __device__ constexpr uint32_t sieve_warp_bytes(uint32_t ring, bool cp) { return ring * kSlotBytes + 16 + 2 * kQueueCap * (cp ? 8u : 4u); }
+constexpr uint32_t kQ2Entry = 16;                    // second queue: position, key (2 words), code point count
+// per warp: ring | pad | first queue (positions) | second queue
+__host__ __device__ constexpr uint32_t sieve_warp_bytes(uint32_t ring, bool cp) { return ring * kSlotBytes + 16 + kQueueCap * 4u + kQueueCap * kQ2Entry; }
 __host__ __device__ constexpr uint32_t sieve_smem_bytes(uint32_t filter_bytes, uint32_t ring, bool cp) {
     return filter_bytes + 16 + kSieveWarps * sieve_warp_bytes(ring, cp);
 }
@@ -126,14 +129,13 @@ template <bool CP, int WC>
 __global__ void __launch_bounds__(kSieveThreads, 1)
 sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_cont, uint32_t *hay_cont, unsigned int *task_counter) {
     extern __shared__ __align__(128) uint8_t smem[];
-    constexpr uint32_t QE = CP ? 8u : 4u;  // queue entry: position [, continuation bytes of the task before its end]
     const uint32_t bloom_s = (uint32_t)__cvta_generic_to_shared(smem);
     const uint32_t bloom_bytes = sv.bloom_words * 4;
     const uint32_t bar_s = bloom_s + bloom_bytes;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t R = P.ring;  // a power of two
     const uint32_t ring_s = bar_s + 16 + warp * sieve_warp_bytes(R, CP);
-    const uint32_t q1_s = ring_s + R * kSlotBytes + 16, q2_s = q1_s + kQueueCap * QE;
+    const uint32_t q1_s = ring_s + R * kSlotBytes + 16, q2_s = q1_s + kQueueCap * 4u;
     const uint32_t n_words = sv.prim_words;              // the primary bitmap (fast path)
     const uint32_t sec_s = bloom_s + sv.prim_words * 4;  // the secondary filter
     const uint32_t sec_words = sv.bloom_words - sv.prim_words;
@@ -172,9 +174,20 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         klo = W <= 4 ? lo >> sh_lo : lo;
         khi = W <= 4 ? 0u : hi >> sh_hi;
     };
-    auto q_store = [&](uint32_t q, uint32_t i, uint32_t rel, uint32_t ce) {
-        asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q + i * QE), "r"(rel) : "memory");
-        if (CP) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q + i * QE + 4), "r"(ce) : "memory");
+    auto q1_store = [&](uint32_t i, uint32_t rel) { asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q1_s + i * 4u), "r"(rel) : "memory"); };
+    // code points: where a ring slot keeps the continuation bytes of its window per 16-byte chunk (32 x u8), and before it (u32)
+    auto slot_s = [&](uint32_t rel) -> uint32_t { return ring_s + ((rel >> 9) & (R - 1)) * kSlotBytes; };
+    // continuation bytes of the task before the END of the candidate at rel (its window is in the ring)
+    auto cont_upto_end = [&](uint32_t rel) -> uint32_t {
+        const uint32_t sl = slot_s(rel), L = (rel & (kWin - 1)) >> 4, k = rel & 15u;
+        uint32_t n = lds32v(sl + kSlotText + 32);
+#pragma unroll
+        for (int w = 0; w < 8; w++) {
+            const int left = (int)L - 4 * w;  // chunks of this word that lie before chunk L
+            const uint32_t mask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u));
+            n = __dp4a(lds32v(sl + kSlotText + 4 * w) & mask, 0x01010101u, n);
+        }
+        return n + cont_prefix(sl + 16 + 16 * L, k + 1);
     };
 
     unsigned int claimed = 0;
@@ -252,25 +265,22 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         };
 
         uint32_t n_emitted = 0, q1n = 0, q2n = 0;
-        uint32_t q1_head = 0, q2_head = 0;  // window index of each queue's first entry (valid while the queue is not empty)
-        uint32_t cp_lane = 0;               // code points: continuation bytes seen by this lane in earlier windows of the task
+        uint32_t q1_head = 0;  // window index of the first queue's first entry (valid while the queue is not empty)
+        uint32_t cp_before = 0;             // code points: continuation bytes of the task before the current window
         uint32_t wrel = wfirst;
 
         // ---- stage 2: exact verification of the first (up to) 32 positions of the second queue ----
         auto round2 = [&]() {
             const uint32_t n = min(q2n, 32u);
             const bool active = lane < n;
-            uint32_t rel = 0, aux = 0;
-            if (active) {
-                rel = lds32v(q2_s + lane * QE);
-                if (CP) aux = lds32v(q2_s + lane * QE + 4);
-            }
+            uint4 ent2 = make_uint4(0, 0, 0, 0);  // position, key (2 words), continuation bytes before the end
+            if (active) ent2 = lds128(q2_s + lane * kQ2Entry);
+            const uint32_t rel = ent2.x, aux = ent2.w;
             int32_t hs;
             const int64_t h = hay_of(active ? rel : max(wrel, lo_r), hs);
             uint32_t best = kSieveNoNode, cnt = 0;
             if (active && (int32_t)rel - (int32_t)(W - 1) >= hs) {
-                uint32_t klo, khi;
-                stash_key(rel, klo, khi);
+                const uint32_t klo = ent2.y, khi = ent2.z;
                 const uint32_t x = klo + khi * kMixHi;
                 uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
                 uint32_t v = kSieveNoNode;
@@ -357,16 +367,12 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 n_emitted += total;
             }
             // pop the round
-            uint2 keep = make_uint2(0, 0);
+            uint4 keep = make_uint4(0, 0, 0, 0);
             const bool mv = 32 + lane < q2n;
-            if (mv) {
-                keep.x = lds32v(q2_s + (32 + lane) * QE);
-                if (CP) keep.y = lds32v(q2_s + (32 + lane) * QE + 4);
-            }
+            if (mv) keep = lds128(q2_s + (32 + lane) * kQ2Entry);
             __syncwarp();
-            if (mv) q_store(q2_s, lane, keep.x, keep.y);
+            if (mv) sts128(q2_s + lane * kQ2Entry, keep);
             q2n -= n;
-            q2_head = __shfl_sync(0xffffffffu, keep.x, 0) >> 9;
             __syncwarp();
         };
 
@@ -375,12 +381,10 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             if (q2n > 32) round2();  // room for 32 survivors
             const uint32_t n = min(q1n, 32u);
             const bool active = lane < n;
-            uint32_t rel = 0, aux = 0;
+            uint32_t rel = 0, klo = 0, khi = 0;
             bool go = false;
             if (active) {
-                rel = lds32v(q1_s + lane * QE);
-                if (CP) aux = lds32v(q1_s + lane * QE + 4);
-                uint32_t klo, khi;
+                rel = lds32v(q1_s + lane * 4u);
                 stash_key(rel, klo, khi);
                 uint32_t x = klo + khi * kMixHi;
                 if (sec_has(x)) {
@@ -405,21 +409,18 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             }
             const uint32_t surv = __ballot_sync(0xffffffffu, go);
             if (surv) {
-                if (go) q_store(q2_s, q2n + __popc(surv & ((1u << lane) - 1u)), rel, aux);
-                if (q2n == 0) q2_head = __shfl_sync(0xffffffffu, rel, __ffs(surv) - 1) >> 9;
+                // survivors take their key (and, code points, their count) along: stage 2 needs nothing from the ring
+                if (go) sts128(q2_s + (q2n + __popc(surv & ((1u << lane) - 1u))) * kQ2Entry, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
                 q2n += __popc(surv);
             }
             // pop the round
-            uint2 keep = make_uint2(0, 0);
+            uint32_t keep = 0;
             const bool mv = 32 + lane < q1n;
-            if (mv) {
-                keep.x = lds32v(q1_s + (32 + lane) * QE);
-                if (CP) keep.y = lds32v(q1_s + (32 + lane) * QE + 4);
-            }
+            if (mv) keep = lds32v(q1_s + (32 + lane) * 4u);
             __syncwarp();
-            if (mv) q_store(q1_s, lane, keep.x, keep.y);
+            if (mv) q1_store(lane, keep);
             q1n -= n;
-            q1_head = __shfl_sync(0xffffffffu, keep.x, 0) >> 9;
+            q1_head = __shfl_sync(0xffffffffu, keep, 0) >> 9;
             __syncwarp();
         };
 
@@ -494,21 +495,23 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             }
             const bool any = __any_sync(0xffffffffu, m1 != 0);
             if (any || starts_inside) {
-                sts128(text_s(wrel) + 16 * lane, cur);
-                __syncwarp();
-                uint32_t exw = 0, wtot = 0, before = 0;
+                const uint32_t sl = slot_s(wrel);
+                sts128(sl + 16 + 16 * lane, cur);
                 if (CP) {
-                    if (wany) exw = warp_excl_scan(wc, lane, &wtot);
-                    before = __reduce_add_sync(0xffffffffu, cp_lane);
+                    asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(sl + kSlotText + lane), "r"(wc) : "memory");
+                    if (lane == 0) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(sl + kSlotText + 32), "r"(cp_before) : "memory");
                 }
+                __syncwarp();
                 if (CP && starts_inside) {
+                    uint32_t exw = 0, wtot = 0;
+                    if (wany) exw = warp_excl_scan(wc, lane, &wtot);
                     // continuation bytes in [lo_r, pos) for pos in [wrel, wrel + 512]; executed by the whole warp
                     auto cont_before = [&](uint32_t pos) -> uint32_t {
                         const uint32_t rl = pos - wrel;
                         const uint32_t L = min(rl >> 4, 31u);
                         const uint32_t ex = __shfl_sync(0xffffffffu, exw, L);
-                        if (wtot == 0) return before;  // (an ASCII window: nothing to add)
-                        return before + ex + cont_prefix(text_s(wrel) + 16 * L, rl - 16 * L);
+                        if (wtot == 0) return cp_before;  // (an ASCII window: nothing to add)
+                        return cp_before + ex + cont_prefix(sl + 16 + 16 * L, rl - 16 * L);
                     };
                     for (;;) {
                         const bool mine = offc >= (int32_t)max(wrel, lo_r) && offc < (int32_t)wend && hb + lane < B.n_haystacks;
@@ -527,26 +530,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                     const uint32_t ex1 = warp_excl_scan(__popc(m1), lane, &tot1);
                     if (q1n + tot1 <= kQueueCap) {
                         uint32_t at = q1n + ex1;
-                        for (uint32_t m = m1; m; m &= m - 1) {
-                            const uint32_t k = __ffs(m) - 1;
-                            uint32_t ce = 0;
-                            if (CP) {
-                                ce = before;
-                                if (wtot) {
-                                    // continuation bytes of this window before the candidate's end: the lanes before, and the own bytes 0..k
-                                    const uint32_t w4[4] = {cur.x, cur.y, cur.z, cur.w};
-                                    uint32_t own = 0;
-#pragma unroll
-                                    for (int w = 0; w < 4; w++) {
-                                        const int left = (int)k + 1 - 4 * w;
-                                        const uint32_t mask = left >= 4 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << (8 * left)) - 1u));
-                                        own += __popc(w4[w] & ~(w4[w] << 1) & 0x80808080u & mask);
-                                    }
-                                    ce += exw + own;
-                                }
-                            }
-                            q_store(q1_s, at++, wrel + 16 * lane + k, ce);
-                        }
+                        for (uint32_t m = m1; m; m &= m - 1) q1_store(at++, wrel + 16 * lane + (__ffs(m) - 1));
                         if (q1n == 0) q1_head = wrel >> 9;
                         q1n += tot1;
                         __syncwarp();
@@ -566,29 +550,21 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                             const uint32_t mL = __shfl_sync(0xffffffffu, m1, L), exL = __shfl_sync(0xffffffffu, ex1, L);
                             uint32_t k = 0;
                             if (active) k = __fns(mL, 0, (int)(g - exL) + 1);
-                            uint32_t ce = 0;
-                            if (CP) {
-                                const uint32_t ex = __shfl_sync(0xffffffffu, exw, L);
-                                ce = before;
-                                if (wtot) ce += ex + cont_prefix(text_s(wrel) + 16 * L, k + 1);
-                            }
-                            if (active) q_store(q1_s, q1n + lane, wrel + 16 * L + k, ce);
+                            if (active) q1_store(q1n + lane, wrel + 16 * L + k);
                             if (q1n == 0) q1_head = wrel >> 9;
                             q1n += min(tot1 - base, 32u);
                             __syncwarp();
                             while (q1n >= 32) round1();
                         }
                     }
-                    while (q2n >= 32) round2();
                 }
             }
-            if (CP) cp_lane += wc;
+            if (CP && wany) cp_before += __reduce_add_sync(0xffffffffu, wc);
             if (wrel >= wlast) break;
             // what is still queued from the window whose ring slot the next window will take has to go now
             {
                 const uint32_t next_w = (wrel >> 9) + 1;
                 while (q1n && q1_head + R <= next_w) round1();
-                while (q2n && q2_head + R <= next_w) round2();
             }
             __syncwarp();  // every lane is done with the slot before its history is replaced
             if (lane == 31) sts128(text_s(wrel + kWin) - 16, cur);
@@ -600,10 +576,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         while (q1n) round1();
         while (q2n) round2();
         if (lane == 0) out.unit_counts[task] = n_emitted;
-        if (CP) {
-            const uint32_t all = __reduce_add_sync(0xffffffffu, cp_lane);
-            if (lane == 0) task_cont[task] = all;
-        }
+        if (CP && lane == 0) task_cont[task] = cp_before;
         __syncwarp();
     }
 }

@@ -173,7 +173,7 @@ uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_
     const uint64_t max_bits = uint64_t(bloom_bytes_max) * 8;
     // The primary bitmap (one bit per W-byte suffix, the only thing the fast path looks at) is kept sparse -- its fill
     // is the share of text positions that need a second look -- but never takes more than 70 % of the budget.
-    uint64_t prim_bits = uint64_t(n_keys) * 64;
+    uint64_t prim_bits = uint64_t(n_keys) * 256;
     if (prim_bits > max_bits * 7 / 10) prim_bits = max_bits * 7 / 10;
     if (prim_bits < 4096) prim_bits = 4096;
     const uint32_t prim_words = (uint32_t)(((prim_bits + 31) / 32 + 3) & ~uint64_t(3));

@@ -153,7 +153,7 @@ class _Automaton:
 
     # ---- the sieve image (position-parallel scan: Bloom filter in shared memory + reverse trie in HBM/L2) ----
     ENGINE = __import__("os").environ.get("ACB200_ENGINE", "sieve")   # "sieve" | "table": default kernel family
-    SIEVE_SMEM_RESERVE = 51 * 1024   # per warp: one window of text + two queues (code point variant); barrier
+    SIEVE_SMEM_RESERVE = 46 * 1024   # 24 warps x (one ring slot of text + two queues); barrier
     SIEVE_W_MAX = 0                  # 0 = the builder chooses the primary window
 
     def sieve(self, device):
