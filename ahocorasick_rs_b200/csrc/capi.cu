@@ -550,6 +550,21 @@ __global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiAr
     }
 }
 
+// ---------------------------------------------------------------------------
+// Multi-GPU: the block a rank contributes to the gather of the match lists --
+// row 0 = (count, haystack base, complete flag, 0), then its first `cap`
+// matches -- assembled by ONE launch straight from a scan's output buffers.
+// ---------------------------------------------------------------------------
+__global__ void pack_gather_block_kernel(const unsigned long long *totals, const acb_match *out, uint32_t hay_base, unsigned long long cap,
+                                         uint4 *block) {
+    const unsigned long long total = totals[0];
+    const unsigned long long n = total < cap ? total : cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        block[0] = make_uint4((uint32_t)(total > 0xffffffffull ? 0xffffffffull : total), hay_base, (uint32_t)totals[1], 0u);
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+        block[1 + i] = reinterpret_cast<const uint4 *>(out)[i];
+}
+
 // when the input is empty: nothing ran, publish zeros
 __global__ void zero_outputs_kernel(unsigned long long *unit_offsets, unsigned long long *match_offsets, int64_t n_haystacks,
                                     unsigned long long *totals) {
@@ -728,9 +743,9 @@ int acb_sieve_describe(const void *host_sieve, acb_sieve_desc *d) {
     return ACB_OK;
 }
 
-// tasks of the sieve kernel: a multiple of 512 bytes (tuning.segment_bytes when the sieve kernel is forced, else 8 KiB)
+// tasks of the sieve kernel: a multiple of 512 bytes (tuning.segment_bytes when the sieve kernel is forced, else 16 KiB)
 static uint32_t sieve_task_bytes() {
-    uint32_t t = (g_tuning.kernel == 5 && g_tuning.segment_bytes > 0) ? (uint32_t)g_tuning.segment_bytes : 8192u;
+    uint32_t t = (g_tuning.kernel == 5 && g_tuning.segment_bytes > 0) ? (uint32_t)g_tuning.segment_bytes : 16384u;
     t = (t + 511u) & ~511u;
     return t < 512u ? 512u : t;
 }
@@ -1029,6 +1044,19 @@ int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *de
     const DevImage im = make_view(h, dev_image);
     const int restart = (!overlapping && h.match_kind == ACB_STANDARD) ? 1 : 0;
     profile_kernel<<<(unsigned)((n_samples + 127) / 128), 128, 0, st>>>(im, B, dev_visits, n_samples, 1024, restart);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return ACB_OK;
+}
+
+int acb_pack_gather_block(const uint64_t *dev_total, const acb_match *dev_out, uint32_t hay_base, uint64_t cap, void *dev_block, void *stream) {
+    if (!dev_total || !dev_out || !dev_block) return fail(ACB_EINVAL, "null argument");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned blocks = (unsigned)((cap + 255) / 256);
+    if (blocks > 296) blocks = 296;
+    if (blocks < 1) blocks = 1;
+    pack_gather_block_kernel<<<blocks, 256, 0, st>>>(reinterpret_cast<const unsigned long long *>(dev_total), dev_out, hay_base, cap,
+                                                     reinterpret_cast<uint4 *>(dev_block));
     g_launches++;
     CUDA_OK(cudaGetLastError());
     return ACB_OK;

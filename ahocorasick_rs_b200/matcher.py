@@ -152,7 +152,8 @@ class _Automaton:
         return img
 
     # ---- the sieve image (position-parallel scan: Bloom filter in shared memory + reverse trie in HBM/L2) ----
-    ENGINE = __import__("os").environ.get("ACB200_ENGINE", "sieve")   # "sieve" | "table": default kernel family
+    ENGINE = __import__("os").environ.get("ACB200_ENGINE", "auto")   # "auto" | "sieve" | "table": kernel family (see scan_device)
+    AUTO_PROFILE_BYTES = 4 << 20     # "auto": inputs below this never pay for the profiling pass
     SIEVE_SMEM_RESERVE = 46 * 1024   # 24 warps x (one ring slot of text + two queues); barrier
     SIEVE_W_MAX = 0                  # 0 = the builder chooses the primary window
 
@@ -333,12 +334,26 @@ class _Automaton:
         # which kernel family: the position-parallel sieve (default) or the table walkers (forced by the tuning knob,
         # or ENGINE = "table").  Results are identical; only the device images a scan needs differ.
         forced = _capi.current_kernel()
-        use_sieve = forced == 5 or (forced == 0 and self.ENGINE == "sieve")
         with self._lock, torch.cuda.device(dev):
+            # Which kernel family.  Results are identical; only speed and the device images a scan needs differ.
+            #   table  the automaton walkers: best when the scan lives in a few hundred states that fit in shared memory
+            #          (sparse matches in text) -- the profile of the data says so (hot-row coverage);
+            #   sieve  the position-parallel filter + exact verification: everything else (dense pattern sets, whose
+            #          states live in L2), and small inputs, where the profiling pass would cost more than the scan.
+            hot = None
+            if forced == 5 or (forced == 0 and self.ENGINE == "sieve"):
+                use_sieve = True
+            elif forced in (1, 2, 3, 4) or self.ENGINE == "table":
+                use_sieve = False
+            else:
+                use_sieve = data.numel() < self.AUTO_PROFILE_BYTES and self._hot.get(dev.index if dev.index is not None else torch.cuda.current_device()) is None
+                if not use_sieve:
+                    hot = self.hot(dev, data, offsets, overlapping)
+                    use_sieve = bool(hot["rows"].reserved & 1)
             if use_sieve:
                 sieve_t, sieve_d = self.sieve(dev)
                 hot = None
-            else:
+            elif hot is None:
                 hot = self.hot(dev, data, offsets, overlapping)
             plan = self._plan(data, n)
             while True:

@@ -67,64 +67,74 @@ class MatchListGather:
     """The same exchange without touching the host: nothing here waits for the
     GPU, so a pipeline of scans keeps running.  Every rank contributes a fixed
     (cap + 1, 4) int32 block -- row 0 = (count, hay_base, complete flag, 0),
-    then its first `cap` matches -- in ONE all_gather per call; the buffers are
-    allocated once.  decode_gathered() turns the result into the ordered global
-    list (that is where the host finally looks at the counts).
+    then its first `cap` matches -- to ONE all_gather per call.  On a GPU the block
+    is assembled by one kernel of the library (acb_pack_gather_block) and the
+    exchange runs on a side stream: the caller's stream never waits for the
+    collective of the step it just enqueued.  The caller alternates `slot` (and the
+    scan's workspace: scan_device(..., ws_slot=slot)) between 0 and 1; the scan that
+    reuses a slot's workspace two steps later is made to wait for that slot's
+    exchange -- long finished by then.  Call finish() before reading the result or
+    timing the stream.  decode_gathered() turns a result into the ordered global
+    list (that is where the host finally looks at the counts)."""
 
-    overlap=True runs the exchange on a side stream: the caller's stream only
-    waits until the matches are copied out of the scan's output buffer (a few
-    microseconds), so the collective's latency overlaps the next scan.  Call
-    finish() before reading the result or timing the stream."""
-
-    def __init__(self, cap: int, device, group=None, overlap: bool = False):
+    def __init__(self, cap: int, device, group=None):
         import torch
         import torch.distributed as dist
 
         self.cap = cap
         self.group = group
         self.world = dist.get_world_size(group)
-        self.block = torch.zeros((cap + 1, 4), dtype=torch.int32, device=device)
-        self.everything = torch.empty(self.world * (cap + 1) * 4, dtype=torch.int32, device=device)
-        self.side = torch.cuda.Stream(device=device) if overlap and device.type == "cuda" else None
+        self.device = device
+        self.cuda = device.type == "cuda"
+        self.blocks = [torch.zeros((cap + 1, 4), dtype=torch.int32, device=device) for _ in range(2)]
+        self.everything = [torch.empty(self.world * (cap + 1) * 4, dtype=torch.int32, device=device) for _ in range(2)]
+        self.side = torch.cuda.Stream(device=device) if self.cuda else None
+        self.done = [None, None]
 
-    def _exchange(self, matches, status, hay_base: int):
-        import torch.distributed as dist
-
-        k = min(self.cap, matches.shape[0])
-        self.block[1: k + 1].copy_(matches[:k])
-        lo = status.view(self.block.dtype)  # little-endian low words of the 64-bit counters
-        head = self.block[0]
-        head[0:1].copy_(lo[0:1])
-        head[2:3].copy_(lo[2:3])
-        head[1:2].fill_(hay_base)
-
-    def __call__(self, matches, status, hay_base: int):
+    def __call__(self, matches, status, hay_base: int, slot: int = 0):
         """matches: the (capacity, 4) int32 output buffer of scan_device(sync=False); status: its
         8-entry int64 device status tensor ([0] = valid rows, [1] = complete flag).
-        Returns the (world, cap + 1, 4) device tensor (reused by the next call)."""
+        Returns the (world, cap + 1, 4) device tensor of this slot (reused two calls later)."""
         import torch
         import torch.distributed as dist
 
-        if self.side is None:
-            self._exchange(matches, status, hay_base)
-            dist.all_gather_into_tensor(self.everything, self.block.view(-1), group=self.group)
-        else:
-            main = torch.cuda.current_stream(matches.device)
-            self.side.wait_stream(main)  # the scan that produced `matches`
-            with torch.cuda.stream(self.side):
-                self._exchange(matches, status, hay_base)
-                copied = torch.cuda.Event()
-                copied.record(self.side)
-                dist.all_gather_into_tensor(self.everything, self.block.view(-1), group=self.group)
-            main.wait_event(copied)      # from here on the scan's buffers may be reused
-        return self.everything.view(self.world, self.cap + 1, 4)
+        block, everything = self.blocks[slot], self.everything[slot]
+        if not self.cuda:
+            # CPU tensors (gloo, tests): the same block, assembled with tensor ops
+            k = min(self.cap, matches.shape[0])
+            block[1: k + 1].copy_(matches[:k])
+            lo = status.view(block.dtype)  # little-endian low words of the 64-bit counters
+            block[0, 0] = lo[0]
+            block[0, 2] = lo[2]
+            block[0, 1] = hay_base
+            dist.all_gather_into_tensor(everything, block.view(-1), group=self.group)
+            return everything.view(self.world, self.cap + 1, 4)
+        from . import _capi
+        main = torch.cuda.current_stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(main)  # the scan that produced `matches`
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            rc = _capi.lib().acb_pack_gather_block(status.data_ptr(), matches.data_ptr(), hay_base, self.cap, block.data_ptr(),
+                                                   self.side.cuda_stream)
+            if rc != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            dist.all_gather_into_tensor(everything, block.view(-1), group=self.group)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            self.done[slot] = ev
+        # the next scan writes the OTHER slot's workspace, which the previous call's exchange read
+        other = self.done[1 - slot]
+        if other is not None:
+            main.wait_event(other)
+        return everything.view(self.world, self.cap + 1, 4)
 
     def finish(self):
-        """Make the caller's stream wait for the exchange in flight (overlap=True)."""
+        """Make the caller's stream wait for the exchanges in flight."""
         import torch
 
         if self.side is not None:
-            torch.cuda.current_stream(self.block.device).wait_stream(self.side)
+            torch.cuda.current_stream(self.device).wait_stream(self.side)
 
 
 def gather_match_lists_async(matches, status, hay_base: int, cap: int, group=None):
@@ -165,7 +175,7 @@ def scan_sharded(scan_fn: Callable, data: np.ndarray, offsets: np.ndarray, group
     return gather_match_lists(local, lo, group=group)
 
 
-def scan_sharded_single(scan_fn: Callable, data: np.ndarray, max_pattern_len: int, group=None, codepoints: bool = False):
+def scan_sharded_single(scan_fn: Callable, data: np.ndarray, max_pattern_len: int, group=None, codepoints: bool = False, device=None):
     """ONE large haystack, overlapping search, across the ranks.  Rank r owns
     the bytes [a_r, b_r) of a contiguous split and scans [a_r - halo, b_r) with
     halo = max_pattern_len - 1: the automaton state depends on no more than that, so the
@@ -178,10 +188,12 @@ def scan_sharded_single(scan_fn: Callable, data: np.ndarray, max_pattern_len: in
     indexes when codepoints=True (the ranks then exchange how many continuation bytes each
     of them owns, to rebase the indexes).  Returns the global (k, 4) int64 tensor
     (0, pattern, start, end) on every rank.  Non-overlapping searches do not shard this way
-    (restarts chain the ranges); the caller must not use this for them."""
+    (restarts chain the ranges); the caller must not use this for them.  `device`: where the exchanged tensors
+    live (None = CPU, for gloo; the CUDA device for NCCL)."""
     import torch
     import torch.distributed as dist
 
+    dev = torch.device("cpu") if device is None else device
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = len(data)
@@ -203,8 +215,8 @@ def scan_sharded_single(scan_fn: Callable, data: np.ndarray, max_pattern_len: in
         if shared < len(window) and is_cont[shared]:
             shared_cp -= 1
         keep = local[:, 3] > shared_cp if rank > 0 else torch.ones(local.shape[0], dtype=torch.bool)
-        owned = torch.tensor([int(is_cont[shared:].sum())], dtype=torch.int64)  # continuation bytes in [a, b)
-        counts = torch.zeros(world, dtype=torch.int64)
+        owned = torch.tensor([int(is_cont[shared:].sum())], dtype=torch.int64, device=dev)  # continuation bytes in [a, b)
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
         dist.all_gather_into_tensor(counts, owned, group=group)
         cont_before_a = int(counts[:rank].sum())
         cont_before_w0 = cont_before_a - int(is_cont[:shared].sum())
@@ -215,14 +227,15 @@ def scan_sharded_single(scan_fn: Callable, data: np.ndarray, max_pattern_len: in
     local[:, 2] += base
     local[:, 3] += base
     # gather with 64-bit records (offsets of a multi-gigabyte haystack): counts first, then padded blocks
-    cnt = torch.tensor([local.shape[0]], dtype=torch.int64)
-    cnts = torch.zeros(world, dtype=torch.int64)
+    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    cnts = torch.zeros(world, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(cnts, cnt, group=group)
+    cnts = cnts.cpu()
     kmax = max(int(cnts.max()), 1)
-    padded = torch.zeros((kmax, 4), dtype=torch.int64)
-    padded[: local.shape[0]] = local
-    everything = torch.zeros(world * kmax * 4, dtype=torch.int64)
+    padded = torch.zeros((kmax, 4), dtype=torch.int64, device=dev)
+    padded[: local.shape[0]] = local.to(dev)
+    everything = torch.zeros(world * kmax * 4, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(everything, padded.view(-1), group=group)
-    everything = everything.view(world, kmax, 4)
+    everything = everything.view(world, kmax, 4).cpu()
     return torch.cat([everything[r, : int(cnts[r])] for r in range(world)], dim=0)
 

@@ -221,6 +221,15 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
                    const void *dev_sieve, const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
                    int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream);
 
+/*
+ * Multi-GPU: the fixed-size block a rank contributes to the gather of the per-shard match lists (the only exchange
+ * of the sharded path; NCCL all-gather over NVLink).  dev_block holds (cap + 1) records of 16 bytes: record 0 =
+ * (match count, hay_base, complete flag, 0), then the first `cap` matches of a finished scan (dev_total / dev_out of
+ * its workspace).  One launch on `stream`, no host round trip.
+ */
+int acb_pack_gather_block(const uint64_t *dev_total, const acb_match *dev_out, uint32_t hay_base, uint64_t cap, void *dev_block,
+                          void *stream);
+
 /* Kernel launch bookkeeping for bench.py's "gpu_launches". */
 uint64_t acb_launch_count(void);
 
