@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstring>
 #include <stdexcept>
+#include <thread>
 
 namespace acb {
 namespace {
@@ -284,10 +285,41 @@ Automaton *build_automaton(const uint8_t *blob, const uint64_t *offsets, uint64_
         return t | ((match_off[t + 1] != match_off[t]) ? kMatchFlag : 0u);
     };
     for (uint32_t c = 0; c < n_cols; c++) T[uint64_t(kRoot) * n_cols + c] = entry(kRoot);  // kDead row stays all kDead
-    for (uint32_t s = kRoot; s < n_states; s++) {
-        uint32_t *row = T + uint64_t(s) * n_cols;
-        if (s != kRoot) std::memcpy(row, T + uint64_t(fail[s]) * n_cols, uint64_t(n_cols) * 4);
-        for (uint32_t c = first_kid[s], e = first_kid[s + 1]; c < e; c++) row[colmap[in_byte[c]]] = entry(c);
+    auto fill_rows = [&](uint32_t lo, uint32_t hi) {
+        for (uint32_t s = lo; s < hi; s++) {
+            uint32_t *row = T + uint64_t(s) * n_cols;
+            if (s != kRoot) std::memcpy(row, T + uint64_t(fail[s]) * n_cols, uint64_t(n_cols) * 4);
+            for (uint32_t c = first_kid[s], e = first_kid[s + 1]; c < e; c++) row[colmap[in_byte[c]]] = entry(c);
+        }
+    };
+    // A row needs its failure target's row, which is strictly shallower: the rows of ONE trie level are independent of
+    // each other, so each level (contiguous in the breadth-first numbering) is filled by several threads.
+    std::vector<uint32_t> level_start;  // first state of each depth, then n_states
+    {
+        std::vector<uint32_t> depth(n_states, 0);
+        level_start.push_back(kRoot);
+        for (uint32_t s = kRoot + 1; s < n_states; s++) {
+            depth[s] = depth[parent[s]] + 1;
+            if (depth[s] != depth[s - 1]) level_start.push_back(s);
+        }
+        level_start.push_back(n_states);
+    }
+    const unsigned hw = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    for (size_t lv = 0; lv + 1 < level_start.size(); lv++) {
+        const uint32_t lo = level_start[lv], hi = level_start[lv + 1];
+        const uint64_t cells = uint64_t(hi - lo) * n_cols;
+        const unsigned nt = cells < (1u << 18) ? 1u : hw;
+        if (nt == 1) {
+            fill_rows(lo, hi);
+            continue;
+        }
+        std::vector<std::thread> pool;
+        const uint32_t per = (hi - lo + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; t++) {
+            const uint32_t a = lo + t * per, b = std::min(hi, a + per);
+            if (a < b) pool.emplace_back(fill_rows, a, b);
+        }
+        for (auto &th : pool) th.join();
     }
     return A;
 }

@@ -668,6 +668,11 @@ class AhoCorasick:
         """Device-resident UTF-8 batch -> (matches, match_offsets, total); code point indexes."""
         return self._ac.scan_device(data, offsets, overlapping, codepoints=True, **kw)
 
+    def scan_host(self, data, offsets, overlapping: bool = False, **kw):
+        """Host-resident UTF-8 batch (uint8 array + int64 offsets) -> host arrays (matches (k, 4), match_offsets (n + 1));
+        code point indexes.  Copies and scans are pipelined (see _Automaton.scan_host)."""
+        return self._ac.scan_host(data, offsets, overlapping, codepoints=True, **kw)
+
 
 class BytesAhoCorasick:
     """Search for multiple pattern bytes against a bytes-like haystack
@@ -703,3 +708,8 @@ class BytesAhoCorasick:
     def scan_device(self, data, offsets, overlapping: bool = False, **kw):
         """Device-resident batch -> (matches, match_offsets, total); byte offsets."""
         return self._ac.scan_device(data, offsets, overlapping, codepoints=False, **kw)
+
+    def scan_host(self, data, offsets, overlapping: bool = False, **kw):
+        """Host-resident batch (uint8 array + int64 offsets) -> host arrays (matches (k, 4), match_offsets (n + 1));
+        byte offsets.  Copies and scans are pipelined (see _Automaton.scan_host)."""
+        return self._ac.scan_host(data, offsets, overlapping, codepoints=False, **kw)
