@@ -1,6 +1,7 @@
 // capi.cu -- the C ABI (include/acb200.h): planning, kernel dispatch, ordering passes.
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -479,8 +480,13 @@ __global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiAr
             E.totals[6] = E.unit_offsets[E.n_tasks];
             E.totals[7] = E.acc[kAccRaw];
         }
+        if (MODE != kModeOverlap) {
+            // the per-haystack selection counts start at zero (the task counts in this array were consumed by phase 2)
+            for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) E.unit_counts[h] = 0;
+        }
     }
     grid.sync();
+    // (from here on unit_counts / unit_offsets are per HAYSTACK: the task-level values have been consumed)
     const unsigned long long list_total = E.totals[6];
     const unsigned long long avail = list_total < E.out_cap ? list_total : E.out_cap;
     if (MODE != kModeOverlap && (list_total > E.out_cap || E.totals[7] > E.raw_cap)) {
@@ -500,8 +506,19 @@ __global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiAr
         return;
     }
     if (MODE == kModeOverlap) {
-        for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x)
-            E.match_offsets[h] = (h == E.B.n_haystacks) ? list_total : first_of_haystack(E.ordered, avail, h);
+        // per-haystack offsets into the list: the first record of every haystack is found where the haystack id changes
+        // (one pass over the records; the haystacks in between, which have no matches, get the same offset)
+        const int64_t nh = E.B.n_haystacks;
+        if (avail == 0) {
+            for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= nh; h += (int64_t)gridDim.x * blockDim.x) E.match_offsets[h] = h == nh ? list_total : 0;
+        } else {
+            for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < avail; i += (unsigned long long)gridDim.x * blockDim.x) {
+                const int64_t hc = (int64_t)E.ordered[i].haystack, hp = i ? (int64_t)E.ordered[i - 1].haystack : -1;
+                for (int64_t h = hp + 1; h <= hc; h++) E.match_offsets[h] = i;
+                if (i + 1 == avail)
+                    for (int64_t h = hc + 1; h <= nh; h++) E.match_offsets[h] = h == nh ? list_total : avail;
+            }
+        }
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             const unsigned long long raw_total = E.acc[kAccRaw];
             E.totals[0] = list_total;
@@ -514,12 +531,17 @@ __global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiAr
         }
         return;
     }
-    // phase 4: per haystack, select the non-overlapping matches and pack them to the front of the haystack's stretch
+    // phase 4: per haystack, select the non-overlapping matches and pack them to the front of the haystack's stretch.
+    // A haystack's stretch starts where the haystack id changes: the thread that sees the change owns it.  (Haystacks
+    // without matches keep the zero count written in phase 3.)
     const uint64_t n_hay = (uint64_t)E.B.n_haystacks;
-    for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h < E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) {
-        const unsigned long long lo = first_of_haystack(E.ordered, avail, h), hi = first_of_haystack(E.ordered, avail, h + 1);
-        E.unit_offsets[h] = lo;
-        E.unit_counts[h] = hi > lo ? select_non_overlapping<MODE>(E.ordered + lo, hi - lo, E.max_pat_len, E.longest) : 0u;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < avail; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t hc = E.ordered[i].haystack;
+        if (i && E.ordered[i - 1].haystack == hc) continue;
+        unsigned long long hi = i + 1;
+        while (hi < avail && E.ordered[hi].haystack == hc) hi++;
+        E.unit_offsets[hc] = i;
+        E.unit_counts[hc] = select_non_overlapping<MODE>(E.ordered + i, hi - i, E.max_pat_len, E.longest);
     }
     grid.sync();
     // phase 5 + 6: per-haystack offsets into the output
@@ -563,6 +585,52 @@ __global__ void pack_gather_block_kernel(const unsigned long long *totals, const
         block[0] = make_uint4((uint32_t)(total > 0xffffffffull ? 0xffffffffull : total), hay_base, (uint32_t)totals[1], 0u);
     for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
         block[1 + i] = reinterpret_cast<const uint4 *>(out)[i];
+}
+
+// ---------------------------------------------------------------------------
+// The non-overlapping selection (select_non_overlapping above) for ONE haystack whose overlapping list was
+// assembled by the caller from several scans (a haystack above one call's 32-bit range): rows of four int64
+// (haystack, pattern, start, end), sorted by (end, start, pattern).  One thread: the selection is a chain.
+// ---------------------------------------------------------------------------
+__global__ void select_rows_kernel(const long long *rows, unsigned long long n, int mode, int longest, long long max_len, long long *out,
+                                   unsigned long long *count) {
+    if (blockIdx.x || threadIdx.x) return;
+    unsigned long long w = 0;
+    long long s = 0;
+    auto put = [&](unsigned long long j) {
+        for (int c = 0; c < 4; c++) out[4 * w + c] = rows[4 * j + c];
+        w++;
+    };
+    if (mode == kModeStandard) {
+        for (unsigned long long i = 0; i < n; i++)
+            if (rows[4 * i + 2] >= s) {
+                s = rows[4 * i + 3];
+                put(i);
+            }
+    } else {
+        unsigned long long i = 0;
+        while (i < n) {
+            bool have = false;
+            unsigned long long best = 0;
+            for (unsigned long long j = i; j < n; j++) {
+                const long long st = rows[4 * j + 2], en = rows[4 * j + 3], pid = rows[4 * j + 1];
+                if (have && en > rows[4 * best + 2] + max_len) break;
+                if (st < s) continue;
+                bool better = !have || st < rows[4 * best + 2];
+                if (have && st == rows[4 * best + 2])
+                    better = longest ? (en > rows[4 * best + 3] || (en == rows[4 * best + 3] && pid < rows[4 * best + 1])) : (pid < rows[4 * best + 1]);
+                if (better) {
+                    best = j;
+                    have = true;
+                }
+            }
+            if (!have) break;
+            s = rows[4 * best + 3];
+            put(best);
+            while (i < n && rows[4 * i + 3] <= s) i++;
+        }
+    }
+    *count = w;
 }
 
 // when the input is empty: nothing ran, publish zeros
@@ -929,6 +997,15 @@ int launch_global(const DevImage &im, const Batch &B, const SegPlan &P, const Si
     return ACB_OK;
 }
 
+inline int epilogue_blocks_per_sm(int max_bps, uint64_t n_units) {
+    static const int forced = [] {
+        const char *e = std::getenv("ACB200_EPILOGUE_BPS");
+        return e ? std::atoi(e) : 0;
+    }();
+    int b = forced > 0 ? forced : (n_units <= (uint64_t(4) << 20) ? 1 : max_bps);
+    return b > max_bps ? max_bps : (b < 1 ? 1 : b);
+}
+
 template <int MODE, bool CP>
 int launch_epilogue(EpilogueArgs &E, const DeviceInfo &d, cudaStream_t st) {
     auto kern = epilogue_kernel<MODE, CP>;
@@ -945,7 +1022,10 @@ int launch_epilogue(EpilogueArgs &E, const DeviceInfo &d, cudaStream_t st) {
         if (bps > 4) bps = 4;
     }
     void *args[] = {&E};
-    CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * bps), dim3(kScanThreads), args, 0, st));
+    // grid-wide barriers cost more the more blocks take part: small jobs (a few hundred thousand units, a few thousand
+    // matches) run one block per SM
+    const int use_bps = epilogue_blocks_per_sm(bps, E.n_units);
+    CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * use_bps), dim3(kScanThreads), args, 0, st));
     g_launches++;
     return ACB_OK;
 }
@@ -1014,7 +1094,9 @@ int launch_sieve_epilogue(SieveEpiArgs &E, const DeviceInfo &d, cudaStream_t st)
         if (bps > 4) bps = 4;
     }
     void *args[] = {&E};
-    CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * bps), dim3(kScanThreads), args, 0, st));
+    const uint64_t n_work = E.n_tasks > (uint64_t)E.B.n_haystacks ? E.n_tasks : (uint64_t)E.B.n_haystacks;
+    const int use_bps = epilogue_blocks_per_sm(bps, n_work);
+    CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * use_bps), dim3(kScanThreads), args, 0, st));
     g_launches++;
     return ACB_OK;
 }
@@ -1049,6 +1131,20 @@ int acb_profile(const acb_automaton *a, const void *dev_image, const uint8_t *de
     return ACB_OK;
 }
 
+int acb_select_non_overlapping(const acb_automaton *a, const int64_t *dev_rows, uint64_t n_rows, int64_t *dev_out, uint64_t *dev_count,
+                                void *stream) {
+    if (!a || !dev_out || !dev_count || (n_rows && !dev_rows)) return fail(ACB_EINVAL, "null argument");
+    const ImageHeader &h = a->impl->hdr;
+    const int kind = (int)h.match_kind;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    select_rows_kernel<<<1, 32, 0, st>>>(reinterpret_cast<const long long *>(dev_rows), n_rows, kind == ACB_STANDARD ? kModeStandard : kModeLeftmost,
+                                         kind == ACB_LEFTMOST_LONGEST ? 1 : 0, (long long)h.max_pat_len, reinterpret_cast<long long *>(dev_out),
+                                         reinterpret_cast<unsigned long long *>(dev_count));
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+    return ACB_OK;
+}
+
 int acb_pack_gather_block(const uint64_t *dev_total, const acb_match *dev_out, uint32_t hay_base, uint64_t cap, void *dev_block, void *stream) {
     if (!dev_total || !dev_out || !dev_block) return fail(ACB_EINVAL, "null argument");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -1069,9 +1165,11 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
     if (n_haystacks > 0xfffffffell) return fail(ACB_EINVAL, "too many haystacks in one batch");
     const ImageHeader &h = a->impl->hdr;
     const int kind = (int)h.match_kind;
-    if (overlapping && kind != ACB_STANDARD)
+    // overlapping == 2: the overlapping LIST, for any match kind -- the input of acb_select_non_overlapping; sieve only
+    if (overlapping == 1 && kind != ACB_STANDARD)
         return fail(ACB_EUNSUPPORTED, std::string("match kind ") + (kind == ACB_LEFTMOST_FIRST ? "LeftmostFirst" : "LeftmostLongest") +
                                           " does not support overlapping searches");
+    if (overlapping == 2 && !dev_sieve) return fail(ACB_EINVAL, "the overlapping list of a leftmost automaton needs the sieve image");
     int rc = check_ws(ws);
     if (rc) return rc;
     DeviceInfo d;
@@ -1113,6 +1211,7 @@ int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *de
 
     int kernel = g_tuning.kernel;
     if (kernel == 0) kernel = dev_sieve ? 5 : 2;  // the caller uploads a sieve image when it wants the position-parallel scan
+    if (overlapping == 2) kernel = 5;
     // the caller's profile says the hot rows do not cover this data: scan from the image in global memory / L2
     if (kernel == 2 && g_tuning.kernel == 0 && hot_desc && (hot_desc->reserved & 1u)) kernel = 4;
     if (kernel == 5 && !dev_sieve) return fail(ACB_EINVAL, "the sieve kernel needs a sieve image (acb_sieve_build / acb_sieve_write)");

@@ -301,9 +301,9 @@ class _Automaton:
         s.dev_match_offsets = ws["match_offsets"].data_ptr()
         return s
 
-    def check_overlapping(self, overlapping: bool):
+    def check_overlapping(self, overlapping):
         # reference: the iterator is refused before any byte is read (src/lib.rs:52-54, 36-39)
-        if overlapping and self.matchkind != MatchKind.Standard:
+        if overlapping and overlapping != 2 and self.matchkind != MatchKind.Standard:
             raise ValueError(f"match kind {self.matchkind.name} does not support overlapping searches")
 
     # ---- scans ------------------------------------------------------------------
@@ -341,7 +341,7 @@ class _Automaton:
             #   sieve  the position-parallel filter + exact verification: everything else (dense pattern sets, whose
             #          states live in L2), and small inputs, where the profiling pass would cost more than the scan.
             hot = None
-            if forced == 5 or (forced == 0 and self.ENGINE == "sieve"):
+            if overlapping == 2 or forced == 5 or (forced == 0 and self.ENGINE == "sieve"):
                 use_sieve = True
             elif forced in (1, 2, 3, 4) or self.ENGINE == "table":
                 use_sieve = False
@@ -363,7 +363,7 @@ class _Automaton:
                                             hot["tensor"].data_ptr() if hot else None, C.byref(hot["rows"]) if hot else None,
                                             sieve_t.data_ptr() if use_sieve else None,
                                             data.data_ptr(), offsets.data_ptr(), n, data.numel(),
-                                            int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(st), stream)
+                                            2 if overlapping == 2 else int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
                     err = _capi.last_error()
                     raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
@@ -393,59 +393,84 @@ class _Automaton:
 
     def _scan_device_windows(self, data, offsets, overlapping, codepoints):
         """scan_device for buffers above WINDOW_BYTES.  Same results, as int64 tensors
-        (offsets no longer fit 32 bits): (matches (k, 4) int64, match_offsets (n + 1) int64, total)."""
+        (offsets no longer fit 32 bits): (matches (k, 4) int64, match_offsets (n + 1) int64, total).
+        Everything stays on the device; the host only learns where the runs of whole haystacks end."""
         torch = _require_cuda()
         dev = data.device
-        offs = offsets.cpu().numpy().astype(np.int64)
-        n = len(offs) - 1
+        n = offsets.numel() - 1
         limit = self.WINDOW_BYTES
         parts = []          # (k, 4) int64 tensors in haystack order
-        counts = np.zeros(n, dtype=np.int64)
+        mo = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+        lens = offsets[1:] - offsets[:-1]
+        oversized = bool((lens > limit).any().item()) if n else False
+        base_count = 0
         h = 0
         while h < n:
-            if offs[h + 1] - offs[h] > limit:
-                part = self._scan_one_large(data[offs[h]:offs[h + 1]], overlapping, codepoints)
+            start = int(offsets[h].item())
+            if oversized and int(lens[h].item()) > limit:
+                part = self._scan_one_large(data[start:start + int(lens[h].item())], overlapping, codepoints)
                 part[:, 0] = h
-                counts[h] = part.shape[0]
                 parts.append(part)
+                base_count += int(part.shape[0])
+                mo[h + 1] = base_count
                 h += 1
                 continue
-            # the longest run of whole haystacks that fits one call
-            h1 = int(np.searchsorted(offs, offs[h] + limit, side="right")) - 1
+            # the longest run of whole haystacks that fits one call (and stops before an oversized one)
+            h1 = int(torch.searchsorted(offsets, torch.tensor([start + limit], dtype=torch.int64, device=dev), right=True).item()) - 1
             h1 = max(h + 1, min(h1, n))
-            sub_offs = torch.from_numpy(offs[h:h1 + 1] - offs[h]).to(dev)
-            m, mo, total = self.scan_device(data[offs[h]:offs[h1]], sub_offs, overlapping, codepoints)
+            if oversized:
+                big = torch.nonzero(lens[h:h1] > limit)
+                if big.numel():
+                    h1 = h + int(big[0].item())
+            end = int(offsets[h1].item())
+            sub_offs = offsets[h:h1 + 1] - start
+            m, mo_run, total = self.scan_device(data[start:end], sub_offs, overlapping, codepoints)
             part = m.to(torch.int64) & 0xFFFFFFFF
             part[:, 0] += h
-            counts[h:h1] = np.diff(mo.cpu().numpy().astype(np.int64))
             parts.append(part)
+            mo[h + 1:h1 + 1] = mo_run[1:h1 - h + 1].to(torch.int64) + base_count
+            base_count += int(total)
             h = h1
-        out = torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
-        mo = np.zeros(n + 1, dtype=np.int64)
-        np.cumsum(counts, out=mo[1:])
-        return out, torch.from_numpy(mo).to(dev), int(out.shape[0])
+        out = torch.cat(parts, dim=0) if len(parts) != 1 else parts[0]
+        if not parts:
+            out = torch.zeros((0, 4), dtype=torch.int64, device=dev)
+        return out, mo, int(out.shape[0])
 
     def _scan_one_large(self, hay, overlapping, codepoints):
-        """One haystack above WINDOW_BYTES (BASELINE config 4: one 4 GiB haystack, overlapping).  Overlapping
-        searches only: windows that share max_pattern_len - 1 bytes are independent (the automaton state depends
-        on no more than that), each keeps the matches that END beyond the shared bytes.  A non-overlapping
-        search restarts at every match end, which chains the windows to each other; that case is refused."""
+        """One haystack above WINDOW_BYTES (BASELINE config 4: one 4 GiB haystack, overlapping).  The OVERLAPPING list
+        is exact window by window: windows that share max_pattern_len - 1 bytes are independent (what ends at a position
+        depends on no more than that), each keeps the matches that END beyond the shared bytes.  A non-overlapping
+        search restarts at every match end, which chains the windows to each other: its result is SELECTED from the
+        overlapping list afterwards (acb_select_non_overlapping), for all three match kinds."""
         torch = _require_cuda()
-        if not overlapping:
-            raise ValueError(f"a single haystack above {self.WINDOW_BYTES} bytes is only supported with overlapping=True "
-                             "(a non-overlapping search cannot be cut into independent windows)")
         dev = hay.device
 
         def scan_window(window):
             one = torch.tensor([0, window.numel()], dtype=torch.int64, device=dev)
-            m, _, _ = self.scan_device(window, one, True, codepoints)
+            m, _, _ = self._scan_overlapping_list(window, one, codepoints)
             return m.to(torch.int64) & 0xFFFFFFFF
 
         parts = scan_in_windows(scan_window, hay, self.WINDOW_BYTES, max(self.max_pattern_len - 1, 0), codepoints)
-        return torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
+        rows = torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)
+        if overlapping or rows.shape[0] == 0:
+            return rows
+        rows = rows.contiguous()
+        out = torch.empty_like(rows)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        rc = self._L.acb_select_non_overlapping(self._h, rows.data_ptr(), rows.shape[0], out.data_ptr(), count.data_ptr(),
+                                                torch.cuda.current_stream(dev).cuda_stream)
+        if rc != _capi.ACB_OK:
+            raise RuntimeError(_capi.last_error())
+        return out[: int(count.item())]
+
+    def _scan_overlapping_list(self, data, offsets, codepoints):
+        """The overlapping match list whatever the automaton's match kind: the sieve's structures do not depend on the
+        kind (overlapping = 2 is the library-internal form of the request; the public overlapping=True on a leftmost
+        automaton stays an error, like the reference's)."""
+        return self.scan_device(data, offsets, 2, codepoints)
 
     # ---- host-resident input (the reference's situation: src/lib.rs:229-249, 422-434 take host str / buffers) ----
-    HOST_CHUNK_BYTES = 64 << 20    # pipeline granularity: copy of chunk i+1 overlaps the scan of chunk i
+    HOST_CHUNK_BYTES = 256 << 20   # pipeline granularity: the copy of run i+1 overlaps the scan of run i and the results of run i-1
     _staging = None                # grow-only pinned staging buffer for inputs that are not pinned already
 
     def _pinned(self, nbytes: int):
@@ -513,10 +538,15 @@ class _Automaton:
                     m, mo2, total = self.scan_device(dbuf[slot][:nbytes], doff[slot][: b - a + 1], overlapping, codepoints,
                                                      capacity=max(total, raw_total) + max(total, raw_total) // 8 + 16, ws_slot=slot)
                     out, mo = m, mo2
-                part = out[:total].cpu().numpy().view(np.uint32).copy()
-                part[:, 0] += a
+                part = np.empty((total, 4), dtype=np.uint32)
+                if total:
+                    torch.from_numpy(part.view(np.int32)).copy_(out[:total])   # one D2H copy straight into the result array
+                    if a:
+                        part[:, 0] += a
                 parts.append(part)
-                counts[a:b] = np.diff(mo[: b - a + 1].cpu().numpy())
+                run_mo = np.empty(b - a + 1, dtype=np.int64)
+                torch.from_numpy(run_mo).copy_(mo[: b - a + 1])
+                counts[a:b] = np.diff(run_mo)
 
             pending = None
             for i, (a, b) in enumerate(runs):

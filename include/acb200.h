@@ -215,11 +215,22 @@ typedef struct acb_workspace {
  * raw_capacity / out_capacity nothing is lost silently: dev_total[1] is 0 and
  * dev_total[0] / [4] say how much room a second call needs.
  * overlapping on a non-Standard automaton returns ACB_EUNSUPPORTED before any
- * byte is read, like the reference.
+ * byte is read, like the reference.  (overlapping = 2 asks for the overlapping LIST of any automaton -- the input of
+ * acb_select_non_overlapping; it needs dev_sieve.)
  */
 int acb_scan_batch(const acb_automaton *a, const void *dev_image, const void *dev_hot, const acb_hot_desc *hot_desc,
                    const void *dev_sieve, const uint8_t *dev_bytes, const int64_t *dev_offsets, int64_t n_haystacks, uint64_t total_bytes,
                    int overlapping, int codepoints, const acb_plan *plan, const acb_workspace *ws, void *stream);
+
+/*
+ * One haystack too large for one call (more than 2^31 bytes), non-overlapping search: the caller scans it as an
+ * OVERLAPPING search in windows (exact: the matches ending at a position depend on max_pattern_len - 1 bytes before it),
+ * concatenates the lists -- rows of four int64 (haystack, pattern, start, end), in the reference's order -- and this call
+ * selects from them what the reference's non-overlapping iterator (try_find_iter, src/lib.rs:58-60) reports for the
+ * automaton's match kind: dev_out gets the selected rows, *dev_count their number.  dev_out needs room for n_rows rows.
+ */
+int acb_select_non_overlapping(const acb_automaton *a, const int64_t *dev_rows, uint64_t n_rows, int64_t *dev_out, uint64_t *dev_count,
+                                void *stream);
 
 /*
  * Multi-GPU: the fixed-size block a rank contributes to the gather of the per-shard match lists (the only exchange

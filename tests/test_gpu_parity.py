@@ -277,10 +277,12 @@ def test_windows_and_runs_match_one_call(monkeypatch):
     ac = BytesAhoCorasick(pats)
     monkeypatch.setattr(matcher._Automaton, "WINDOW_BYTES", 30_001)
     got = ac.find_matches_as_indexes(hay.tobytes(), overlapping=True)
-    with pytest.raises(ValueError):
-        ac.find_matches_as_indexes(hay.tobytes())          # non-overlapping: refused for a single oversized haystack
+    # non-overlapping on a single oversized haystack: selected from the windows' overlapping lists, every match kind
+    non = {kind: BytesAhoCorasick(pats, kind).find_matches_as_indexes(hay.tobytes()) for kind in KINDS}
     monkeypatch.undo()
     assert got == exp
+    for kind in KINDS:
+        assert non[kind] == Oracle(pats, kind.name).find(hay.tobytes()), kind
     text = "".join(rng.choice(list("ab—é☃cd"), size=60_000))
     upats = ["a—", "—é", "☃c", "b", "é☃c", "dd"]
     ref = AhoCorasick(upats).find_matches_as_indexes(text, overlapping=True)
