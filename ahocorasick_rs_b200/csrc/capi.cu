@@ -489,8 +489,9 @@ __global__ void __launch_bounds__(kScanThreads) sieve_epilogue_kernel(SieveEpiAr
     // (from here on unit_counts / unit_offsets are per HAYSTACK: the task-level values have been consumed)
     const unsigned long long list_total = E.totals[6];
     const unsigned long long avail = list_total < E.out_cap ? list_total : E.out_cap;
-    if (MODE != kModeOverlap && (list_total > E.out_cap || E.totals[7] > E.raw_cap)) {
-        // The buffers were too small: the ordered list has holes (stale records), nothing may be selected from it.
+    if (list_total > E.out_cap || E.totals[7] > E.raw_cap) {
+        // The buffers were too small: the ordered list has holes (stale records): nothing may be read from it, not even
+        // the haystack ids for the per-haystack offsets.
         // Report how much room is needed; the caller retries.  (Every block takes this branch: totals[6..7] were
         // published before the barrier and nobody writes them again.)
         for (int64_t h = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; h <= E.B.n_haystacks; h += (int64_t)gridDim.x * blockDim.x) E.match_offsets[h] = 0;
@@ -1002,7 +1003,8 @@ inline int epilogue_blocks_per_sm(int max_bps, uint64_t n_units) {
         const char *e = std::getenv("ACB200_EPILOGUE_BPS");
         return e ? std::atoi(e) : 0;
     }();
-    int b = forced > 0 ? forced : (n_units <= (uint64_t(4) << 20) ? 1 : max_bps);
+    (void)n_units;
+    int b = forced > 0 ? forced : max_bps;  // (one block per SM was measured: 214 vs 197 us per config-2 step -- more blocks win)
     return b > max_bps ? max_bps : (b < 1 ? 1 : b);
 }
 
@@ -1022,8 +1024,6 @@ int launch_epilogue(EpilogueArgs &E, const DeviceInfo &d, cudaStream_t st) {
         if (bps > 4) bps = 4;
     }
     void *args[] = {&E};
-    // grid-wide barriers cost more the more blocks take part: small jobs (a few hundred thousand units, a few thousand
-    // matches) run one block per SM
     const int use_bps = epilogue_blocks_per_sm(bps, E.n_units);
     CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(kern), dim3(d.sms * use_bps), dim3(kScanThreads), args, 0, st));
     g_launches++;

@@ -31,8 +31,10 @@ class MatchKind(enum.Enum):
 
 
 class Implementation(enum.Enum):
-    """reference: src/lib.rs:111-118.  Here: device table layout hint only;
-    results are identical for every value (tests/test_ac.py:22-56)."""
+    """reference: src/lib.rs:111-118.  Here, as there, a table-format choice that never changes results
+    (tests/test_ac.py:22-56): DFA = the dense transition table (walked by the staged / L2 kernels when the data
+    suits them), the two NFA values = the compact sieve image (filters + reverse trie, csrc/sieve.h); None = the
+    library decides from a profile of the data."""
     NoncontiguousNFA = 0
     ContiguousNFA = 1
     DFA = 2
@@ -117,6 +119,7 @@ class _Automaton:
         self._h = h
         self._L = L
         self.matchkind = matchkind
+        self.implementation = implementation
         self.n_patterns = n
         self.num_states = int(L.acb_num_states(h))
         self.num_columns = int(L.acb_num_columns(h))
@@ -345,6 +348,8 @@ class _Automaton:
                 use_sieve = True
             elif forced in (1, 2, 3, 4) or self.ENGINE == "table":
                 use_sieve = False
+            elif self.implementation in (Implementation.ContiguousNFA, Implementation.NoncontiguousNFA):
+                use_sieve = True   # the caller asked for a compact (non-DFA) table format: that is the sieve image
             else:
                 use_sieve = data.numel() < self.AUTO_PROFILE_BYTES and self._hot.get(dev.index if dev.index is not None else torch.cuda.current_device()) is None
                 if not use_sieve:
@@ -470,7 +475,8 @@ class _Automaton:
         return self.scan_device(data, offsets, 2, codepoints)
 
     # ---- host-resident input (the reference's situation: src/lib.rs:229-249, 422-434 take host str / buffers) ----
-    HOST_CHUNK_BYTES = 256 << 20   # pipeline granularity: the copy of run i+1 overlaps the scan of run i and the results of run i-1
+    HOST_CHUNK_BYTES = 1 << 30     # inputs up to this size go in one piece (the scan is ~100x faster than PCIe: nothing to hide);
+                                   # larger ones in runs of this size: copy of run i+1 || scan of run i || results of run i-1
     _staging = None                # grow-only pinned staging buffer for inputs that are not pinned already
 
     def _pinned(self, nbytes: int):
