@@ -127,7 +127,8 @@ class _Automaton:
         self._images = {}      # device index -> uint8 tensor
         self._sieves = {}      # device index -> (uint8 tensor, SieveDesc)
         self._hot = {}         # device index -> dict(tensor, rows, reprofile, calls, backoff)
-        self._ws = {}          # device index -> dict of tensors
+        self._ws = {}          # (device index, slot) -> dict of tensors
+        self._small = {}       # device index -> the small-call context
         self.last_stats = {}
         self._lock = threading.Lock()
         self._host_lock = threading.RLock()   # host-buffer calls: staging buffer + workspaces until the results are on the host
@@ -371,6 +372,7 @@ class _Automaton:
                                             2 if overlapping == 2 else int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(st), stream)
                 if rc != _capi.ACB_OK:
                     err = _capi.last_error()
+                    ws["scratch"][:8].zero_()   # a scan that failed half way may have left its counters dirty
                     raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
                 if not sync:
                     return ws["out"], ws["match_offsets"][: n + 1], ws["total"]
@@ -585,6 +587,86 @@ class _Automaton:
             np.cumsum(counts, out=mo[1:])
             return m, mo
 
+    # ---- one small haystack per call: the reference's own usage (benchmarks/test_comparison.py:119-122) ----
+    SMALL_CALL_BYTES = 256 << 10   # up to here a single-haystack call takes the lean path below
+    SMALL_CALL_ROWS = 64           # matches copied back with the status words in ONE transfer (more: a second copy)
+
+    def _small_ctx(self, dev):
+        """Everything a small call needs, allocated once per device: pinned and device input buffers (offsets first,
+        then the bytes), a workspace whose status words and output rows are adjacent (one D2H copy fetches both), its
+        ctypes description, the sieve image."""
+        torch = _torch()
+        idx = dev.index
+        ctx = self._small.get(idx)
+        if ctx is None:
+            cap_b = self.SMALL_CALL_BYTES
+            sieve_t, sieve_d = self.sieve(dev)
+            img = self.image(dev)
+            h_in = torch.zeros(16 + cap_b + 16, dtype=torch.uint8, pin_memory=True)
+            d_in = torch.zeros(16 + cap_b + 16, dtype=torch.uint8, device=dev)
+            plan = _capi.Plan()
+            if self._L.acb_plan_scan(self._h, d_in.data_ptr() + 16, cap_b, 1, C.byref(plan)) != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            cap = 4096
+            n_units = int(plan.n_units) + 8
+            res = torch.zeros(8 + 2 * cap, dtype=torch.int64, device=dev)
+            ws = {
+                "n_units": n_units, "n_segments": int(plan.n_segments) + 4, "n_haystacks": 1, "capacity": cap,
+                "raw": torch.empty((cap, 4), dtype=torch.int32, device=dev),
+                "raw_seq": torch.empty(cap, dtype=torch.int32, device=dev),
+                "raw_unit": torch.empty(cap, dtype=torch.int32, device=dev),
+                "raw_aux": torch.empty(cap, dtype=torch.int32, device=dev),
+                "unit_counts": torch.empty(n_units, dtype=torch.int32, device=dev),
+                "unit_offsets": torch.empty(n_units + 1, dtype=torch.int64, device=dev),
+                "seg_info": torch.empty((int(plan.n_segments) + 4, 8), dtype=torch.int32, device=dev),
+                "scratch": torch.zeros(int(plan.scratch_words) + 64, dtype=torch.int64, device=dev),
+                "total": res[:8], "out": res[8:].view(torch.int32).view(cap, 4),
+                "match_offsets": torch.empty(2, dtype=torch.int64, device=dev),
+            }
+            ctx = {"h_in": h_in, "d_in": d_in, "hv": h_in.numpy(), "res": res, "ws": ws, "st": self._ws_struct(ws),
+                   "h_res": torch.zeros(8 + 2 * self.SMALL_CALL_ROWS, dtype=torch.int64, pin_memory=True),
+                   "sieve": sieve_t, "img": img, "plan": plan, "max_scratch": int(plan.scratch_words) + 64, "max_units": n_units}
+            ctx["hr"] = ctx["h_res"].numpy()
+            self._small[idx] = ctx
+        return ctx
+
+    def _small_call(self, hay, overlapping: bool, codepoints: bool):
+        """One haystack of at most SMALL_CALL_BYTES (a bytes-like object): one H2D copy, scan + epilogue, one D2H copy of
+        (status, first rows), one synchronisation.  -> uint32 (k, 4) host array."""
+        torch = _require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        n = len(hay)
+        with self._host_lock:
+            ctx = self._small_ctx(dev)
+            hv = ctx["hv"]
+            hv[:16].view(np.int64)[:] = (0, n)
+            if n:
+                hv[16:16 + n] = np.frombuffer(hay, dtype=np.uint8)
+            d_in = ctx["d_in"]
+            d_in[:16 + n].copy_(ctx["h_in"][:16 + n], non_blocking=True)
+            plan = ctx["plan"]
+            base = d_in.data_ptr()
+            if self._L.acb_plan_scan(self._h, base + 16, n, 1, C.byref(plan)) != _capi.ACB_OK:
+                raise RuntimeError(_capi.last_error())
+            if plan.scratch_words > ctx["max_scratch"] or plan.n_units > ctx["max_units"]:
+                return None   # (a tuning knob changed the plan beyond what was allocated: let the general path do it)
+            stream = torch.cuda.current_stream(dev)
+            rc = self._L.acb_scan_batch(self._h, ctx["img"].data_ptr(), None, None, ctx["sieve"].data_ptr(), base + 16, base, 1, n,
+                                        int(bool(overlapping)), int(bool(codepoints)), C.byref(plan), C.byref(ctx["st"]), stream.cuda_stream)
+            if rc != _capi.ACB_OK:
+                err = _capi.last_error()
+                ctx["ws"]["scratch"][:8].zero_()   # a scan that failed half way may have left its counters dirty
+                raise (ValueError if rc == _capi.ACB_EUNSUPPORTED else RuntimeError)(err)
+            ctx["h_res"].copy_(ctx["res"][: ctx["h_res"].numel()], non_blocking=True)
+            stream.synchronize()
+            hr = ctx["hr"]
+            total, complete = int(hr[0]), int(hr[1])
+            if not complete:
+                return None   # more matches than the small workspace holds: the general path sizes one
+            if total <= self.SMALL_CALL_ROWS:
+                return hr[8:8 + 2 * total].view(np.uint32).reshape(total, 4).copy()
+            return ctx["ws"]["out"][:total].cpu().numpy().view(np.uint32)
+
     def scan_host_batch(self, chunks: Sequence[bytes], overlapping: bool, codepoints: bool):
         """Host buffers (bytes-like objects, one per haystack) in, host numpy out: (matches uint32 (k,4),
         match_offsets int64 (n+1)).  The haystacks are gathered into this automaton's pinned staging buffer
@@ -592,6 +674,10 @@ class _Automaton:
         torch = _require_cuda()
         self.check_overlapping(overlapping)
         n = len(chunks)
+        if n == 1 and len(chunks[0]) <= self.SMALL_CALL_BYTES and _capi.current_kernel() in (0, 5) and self.ENGINE != "table":
+            m = self._small_call(chunks[0], overlapping, codepoints)
+            if m is not None:
+                return m, np.array([0, m.shape[0]], dtype=np.int64)
         lens = np.fromiter((len(c) for c in chunks), dtype=np.int64, count=n)
         offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(lens, out=offs[1:])
