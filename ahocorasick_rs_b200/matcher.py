@@ -59,11 +59,12 @@ def _count_cont(x) -> int:
 
 def scan_in_windows(scan_window, hay, window_bytes: int, halo: int, codepoints: bool):
     """An OVERLAPPING search over one haystack too large for one call, as independent windows that share `halo` =
-    max_pattern_len - 1 bytes (the automaton state depends on no more than that).  scan_window(window) returns the
-    window's matches as rows (haystack, pattern, start, end), window-relative, byte offsets or code point indexes.
-    Every window keeps the matches that END beyond the bytes it shares with its predecessor (those were reported,
-    whole, by the predecessor), rebased to the haystack.  `hay` is a uint8 numpy array or torch tensor; returns the
-    list of per-window row blocks, in order (concatenated they are in the reference's order)."""
+    max_pattern_len - 1 bytes (what ends at a position depends on no more than that).  scan_window(window) returns the
+    window's matches as int64 rows (haystack, pattern, start, end), window-relative, byte offsets or code point indexes,
+    sorted by end.  Every window keeps the matches that END beyond the bytes it shares with its predecessor (those were
+    reported, whole, by the predecessor) -- a suffix of its sorted rows --, rebased to the haystack.  `hay` is a uint8
+    numpy array or torch tensor; returns the list of per-window row blocks, in order (concatenated they are in the
+    reference's order)."""
     total_len = len(hay)
     step = window_bytes - halo
     if step <= 0:
@@ -76,19 +77,25 @@ def scan_in_windows(scan_window, hay, window_bytes: int, halo: int, codepoints: 
         window = hay[w0:w1]
         part = scan_window(window)
         if w0 > 0 and part.shape[0]:
+            cut = halo
             if codepoints:
                 # the same cut in code points: ends are character boundaries, so "byte end > halo" is "code point
                 # end > code points that start before byte `halo`" -- minus one when a character straddles that
                 # byte (its end is beyond the shared bytes although no new character starts in between)
-                shared_cp = halo - _count_cont(window[:halo])
+                cut = halo - _count_cont(window[:halo])
                 if halo < len(window) and (int(window[halo]) & 0xC0) == 0x80:
-                    shared_cp -= 1
-                part = part[part[:, 3] > shared_cp]
+                    cut -= 1
+            ends = part[:, 3]
+            if hasattr(ends, "contiguous"):   # torch: the rows are sorted by end, the kept ones are a suffix
+                import torch
+                k0 = int(torch.searchsorted(ends.contiguous(), torch.tensor([cut], dtype=ends.dtype, device=ends.device), right=True).item())
             else:
-                part = part[part[:, 3] > halo]
+                k0 = int(np.searchsorted(ends, cut, side="right"))
+            part = part[k0:]
         base = (w0 - cont_before) if codepoints else w0
-        part[:, 2] += base
-        part[:, 3] += base
+        if base:
+            part[:, 2] += base
+            part[:, 3] += base
         parts.append(part)
         if w1 == total_len:
             break
@@ -396,7 +403,7 @@ class _Automaton:
 
     # One kernel call addresses its buffer with 32-bit offsets.  Larger inputs are cut up here: a batch into
     # runs of whole haystacks, a single haystack above the limit into overlapping windows.
-    WINDOW_BYTES = (1 << 31)
+    WINDOW_BYTES = (1 << 31) - (1 << 16)   # (below 2^31: every offset of one call is a non-negative int32)
 
     def _scan_device_windows(self, data, offsets, overlapping, codepoints):
         """scan_device for buffers above WINDOW_BYTES.  Same results, as int64 tensors
@@ -432,8 +439,9 @@ class _Automaton:
             end = int(offsets[h1].item())
             sub_offs = offsets[h:h1 + 1] - start
             m, mo_run, total = self.scan_device(data[start:end], sub_offs, overlapping, codepoints)
-            part = m.to(torch.int64) & 0xFFFFFFFF
-            part[:, 0] += h
+            part = m.to(torch.int64)
+            if h:
+                part[:, 0] += h
             parts.append(part)
             mo[h + 1:h1 + 1] = mo_run[1:h1 - h + 1].to(torch.int64) + base_count
             base_count += int(total)
@@ -455,7 +463,7 @@ class _Automaton:
         def scan_window(window):
             one = torch.tensor([0, window.numel()], dtype=torch.int64, device=dev)
             m, _, _ = self._scan_overlapping_list(window, one, codepoints)
-            return m.to(torch.int64) & 0xFFFFFFFF
+            return m.to(torch.int64)
 
         parts = scan_in_windows(scan_window, hay, self.WINDOW_BYTES, max(self.max_pattern_len - 1, 0), codepoints)
         rows = torch.cat(parts, dim=0) if parts else torch.zeros((0, 4), dtype=torch.int64, device=dev)

@@ -31,10 +31,11 @@ def partition_by_bytes(offsets: np.ndarray, world: int) -> List[Tuple[int, int]]
 
 
 def gather_match_lists(local, hay_base: int, group=None, dst: Optional[int] = None):
-    """local: (k, 4) int32 tensor (haystack, pattern, start, end) with shard-local
+    """local: (k, 4) int32 or int64 tensor (haystack, pattern, start, end) with shard-local
     haystack ids.  Returns the global list (haystack ids rebased by each rank's
     hay_base) on every rank (dst=None) or on rank `dst` only (others get None).
-    Two collectives: all_gather of the counts, then a padded all_gather."""
+    Two collectives: all_gather of the counts, then an all_gather padded to the longest list
+    (no zero-filling, no per-rank copies: the bases are added in place on the gathered buffer)."""
     import torch
     import torch.distributed as dist
 
@@ -44,23 +45,27 @@ def gather_match_lists(local, hay_base: int, group=None, dst: Optional[int] = No
     meta = torch.tensor([local.shape[0], hay_base], dtype=torch.int64, device=dev)
     metas = torch.empty(world * 2, dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(metas, meta, group=group)
-    metas = metas.view(world, 2)
-    counts = metas[:, 0].tolist()
-    bases = metas[:, 1].tolist()
+    metas = metas.view(world, 2).tolist()
+    counts = [int(c) for c, _ in metas]
+    bases = [int(b) for _, b in metas]
     kmax = max(max(counts), 1)
-    padded = torch.zeros((kmax, 4), dtype=torch.int32, device=dev)
-    padded[: local.shape[0]] = local
-    everything = torch.empty(world * kmax * 4, dtype=torch.int32, device=dev)
+    if local.shape[0] == kmax and local.is_contiguous():
+        padded = local
+    else:
+        padded = torch.empty((kmax, 4), dtype=local.dtype, device=dev)
+        padded[: local.shape[0]] = local
+    everything = torch.empty(world * kmax * 4, dtype=local.dtype, device=dev)
     dist.all_gather_into_tensor(everything, padded.view(-1), group=group)
     everything = everything.view(world * kmax, 4)
     if dst is not None and rank != dst:
         return None
     parts = []
     for r in range(world):
-        part = everything[r * kmax: r * kmax + counts[r]].clone()
-        part[:, 0] += int(bases[r])
+        part = everything[r * kmax: r * kmax + counts[r]]
+        if bases[r]:
+            part[:, 0] += bases[r]
         parts.append(part)
-    return torch.cat(parts, dim=0)
+    return parts[0] if world == 1 else torch.cat(parts, dim=0)
 
 
 class MatchListGather:
