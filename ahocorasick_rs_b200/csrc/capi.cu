@@ -1071,6 +1071,8 @@ int launch_sieve(const DevSieve &sv, const Batch &B, SievePlan &P, const Sink &o
         ACB_SIEVE_GO(0);
     else if (sv.W == 4)
         ACB_SIEVE_GO(1);
+    else if (sv.W == 5)
+        ACB_SIEVE_GO(3);
     else
         ACB_SIEVE_GO(2);
 #undef ACB_SIEVE_GO

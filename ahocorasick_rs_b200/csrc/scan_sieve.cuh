@@ -122,7 +122,7 @@ __device__ __forceinline__ uint32_t warp_excl_scan(uint32_t v, uint32_t lane, ui
     return x - v;
 }
 
-// WC: 0 = W < 4 (the window word is shifted down), 1 = W == 4, 2 = W in 5..8 (two words)
+// WC: 0 = W < 4 (the window word is shifted down), 1 = W == 4, 2 = W in 6..8 (two words), 3 = W == 5 (a word and a byte)
 //
 // Positions inside a task are 32-bit offsets from the task's start (`rel`); the 64-bit stream position is t_lo + rel.
 template <bool CP, int WC>
@@ -456,7 +456,10 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 const int j = 2 + (k >> 2), r = k & 3;
                 const uint32_t wlo = r == 3 ? a[j] : __funnelshift_r(a[j - 1], a[j], 8 * (r + 1));
                 uint32_t x;
-                if (WC == 2) {
+                if (WC == 3) {
+                    // W == 5: the one byte before the 4-byte window, picked straight out of its word
+                    x = wlo + __byte_perm(a[1 + (k >> 2)], 0u, 0x4440u | (uint32_t)r) * kMixHi;
+                } else if (WC == 2) {
                     const uint32_t whi = r == 3 ? a[j - 1] : __funnelshift_r(a[j - 2], a[j - 1], 8 * (r + 1));
                     x = wlo + (whi >> sh_hi) * kMixHi;
                 } else if (WC == 1) {

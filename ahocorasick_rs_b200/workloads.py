@@ -2,14 +2,14 @@
 scalable.  Used by bench.py (full size) and the parity tests (scaled down).
 Everything is generated on the host with numpy; nothing here reads
 /root/reference (the two data fixtures it needs are committed under
-tests/golden/ by tests/golden/make_fixtures.py)."""
+ahocorasick_rs_b200/data/ by tests/golden/make_fixtures.py)."""
 from __future__ import annotations
 
 import os
 
 import numpy as np
 
-_GOLDEN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")   # the two input-data fixtures of config 2
 
 
 def patterns_long():

@@ -186,6 +186,31 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def make_dense(pats, data, offs, seed=7):
+    """The dense-match variant: pattern number (j mod n) written at every 64th byte of every haystack, where that
+    overwrites ASCII bytes only (keeps the text valid UTF-8) and fits inside the haystack."""
+    data = data.copy()
+    lens = np.array([len(p) for p in pats])
+    maxlen = int(lens.max())
+    blob = np.zeros((len(pats), maxlen), dtype=np.uint8)
+    for i, p in enumerate(pats):
+        blob[i, : len(p)] = np.frombuffer(p, dtype=np.uint8)
+    n = len(offs) - 1
+    hay_len = int(offs[1] - offs[0])
+    assert np.all(np.diff(offs) == hay_len), "dense variant: equal-length haystacks"
+    rows = data.reshape(n, hay_len)
+    j = 0
+    for at in range(32, hay_len - maxlen, 64):
+        pid = (np.arange(n) + j) % len(pats)
+        ok = (rows[:, at:at + maxlen] < 0x80).all(axis=1) & (rows[:, at - 1] < 0x80) & (rows[:, at + maxlen] < 0x80) if at + maxlen < hay_len else np.zeros(n, bool)
+        for ln in np.unique(lens):
+            sel = ok & (lens[pid] == ln)
+            if sel.any():
+                rows[sel, at:at + ln] = blob[pid[sel], :ln]
+        j += 1
+    return data
+
+
 # ------------------------------------------------------------------------------------------------ device workloads
 def device_random_lowercase(torch, dev, n_bytes: int, seed: int):
     g = torch.Generator(device=dev)
@@ -205,6 +230,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--dense", action="store_true", help="configs 2 and 3: the dense-match variant (a pattern written every 64 bytes: ~1 match per 64 B), "
+                                                           "to expose the output path (SURVEY.md 8d)")
     ap.add_argument("--scale", type=float, default=1.0, help=argparse.SUPPRESS)       # shrink the workload (development only)
     ap.add_argument("--haystacks", type=int, default=0, help=argparse.SUPPRESS)
     ap.add_argument("--no-cpu-baseline", action="store_true", help=argparse.SUPPRESS)
@@ -255,12 +282,16 @@ def main():
         n_hay = args.haystacks or int(100_000 * args.scale)
         for b in range(2):  # two different batches alternate
             pats, data, offs = host_sample(2, n_hay, first=(rank * 2 + b) * n_hay)
+            if args.dense:
+                data = make_dense(pats, data, offs)
             host_batches.append((data, offs))
         ac = AhoCorasick([p.decode() for p in pats], implementation=Implementation.DFA)
         d_batches = [(torch.from_numpy(d).to(dev), torch.from_numpy(o).to(dev)) for d, o in host_batches]
     elif cfg == 3:
         n_hay = args.haystacks or int(1_000_000 * args.scale)
         pats, data, offs = host_sample(3, n_hay, rank=rank)
+        if args.dense:
+            data = make_dense(pats, data, offs)
         host_batches.append((data, offs))
         ac = BytesAhoCorasick(pats, kind)
         d_batches = [(torch.from_numpy(data).to(dev), torch.from_numpy(offs).to(dev))]
@@ -458,7 +489,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic",
-        "config": {"workload": C["workload"], "haystacks_per_gpu": n_hay, "bytes_per_gpu_per_step": bytes_per_step,
+        "config": {"workload": C["workload"] + (" -- DENSE variant: a pattern written every 64 bytes" if args.dense else ""), "haystacks_per_gpu": n_hay, "bytes_per_gpu_per_step": bytes_per_step,
                    "l2": f"inputs ({bytes_per_step / 1e6:.1f} MB per batch{', two batches alternating' if len(d_batches) > 1 else ''}) are larger than L2; no flush needed",
                    "multi_gpu": "one process per GPU, batch sharded by haystack index, tables replicated; per step one gather of the match lists (NCCL)"},
         "matches_per_s": matches_per_step * args.steps * world / (ms_max * 1e-3),

@@ -167,7 +167,7 @@ def test_never_converging_repair_chain():
 
 
 def test_names_automaton_shape_and_parity():
-    pats = [l.strip().encode() for l in open(os.path.join(HERE, "golden", "patterns_long.txt"))]
+    pats = [l.strip().encode() for l in open(os.path.join(os.path.dirname(HERE), "ahocorasick_rs_b200", "data", "patterns_long.txt"))]
     im = ii.Image(pats, 0, 2)
     assert im.n_states == 11163 + 1          # 11 163 trie states (+ the dead state)
     assert im.col_mode == 0 and im.n_cols == 27 and im.col_lo == ord("a")
