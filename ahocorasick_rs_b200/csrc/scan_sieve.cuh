@@ -284,19 +284,20 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 const uint32_t x = klo + khi * kMixHi;
                 uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
                 uint32_t v = kSieveNoNode;
+                uint2 na = make_uint2(0, 0);
                 for (;;) {
                     const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
                     if (ent.z == kSieveNoNode) break;
                     if (ent.x == klo && ent.y == khi) {
                         v = ent.z;
+                        const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s) + 1);  // same sector: the node's walk record
+                        na = make_uint2(rec.x, rec.y);
                         break;
                     }
                     s = (s + 1) & (sv.ht_size - 1);
                 }
                 // walk towards the pattern start: node v = the d bytes that end at rel
                 uint32_t d = W;
-                uint2 na = make_uint2(0, 0);
-                if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
                 while (v != kSieveNoNode) {
                     if (na.y & kNodeTerminal) best = v;
                     const uint32_t nk = (na.y >> 8) & 0x1ffu;

@@ -102,11 +102,14 @@ struct SieveHeader {
     uint64_t total_bytes;
 };
 
-// hash table: W-byte suffix -> reverse-trie node of depth W
+// hash table: W-byte suffix -> reverse-trie node of depth W.  One 32-byte sector per slot: the node's walk record
+// rides along, so a hit costs ONE dependent access before the children are looked at.
 struct SieveSlot {
     uint32_t key_lo, key_hi;  // the window's bytes (as sieve_x sees them: lo', hi'), exact
     uint32_t node;            // kSieveNoNode = empty
     uint32_t pad;
+    uint32_t first_kid, meta; // copy of the node's SieveNodeA
+    uint32_t pad1, pad2;
 };
 
 // Reverse trie, nodes of depth >= W, children of a node contiguous and sorted by byte.
