@@ -284,7 +284,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 const uint32_t x = klo + khi * kMixHi;
                 uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
                 uint32_t v = kSieveNoNode;
-                uint2 na = make_uint2(0, 0);
+                uint2 na = make_uint2(0, 0), only_kid = make_uint2(0, 0);
                 for (;;) {
                     const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
                     if (ent.z == kSieveNoNode) break;
@@ -292,6 +292,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                         v = ent.z;
                         const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s) + 1);  // same sector: the node's walk record
                         na = make_uint2(rec.x, rec.y);
+                        only_kid = make_uint2(rec.z, rec.w);
                         break;
                     }
                     s = (s + 1) & (sv.ht_size - 1);
@@ -305,7 +306,13 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                     const uint32_t b = __ldg(tptr + ((int64_t)(int32_t)rel - (int64_t)d));
                     uint32_t c = kSieveNoNode;
                     uint2 nc = make_uint2(0, 0);
-                    if (nk <= 8) {
+                    if (d == W && nk == 1) {
+                        // the slot brought the only child along: no access at all when the byte does not continue the pattern
+                        if ((only_kid.y & 0xffu) == b) {
+                            c = na.x;
+                            nc = only_kid;
+                        }
+                    } else if (nk <= 8) {
                         for (uint32_t t = 0; t < nk; t++) {
                             const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
                             const uint32_t cb = cand.y & 0xffu;
@@ -411,7 +418,12 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             const uint32_t surv = __ballot_sync(0xffffffffu, go);
             if (surv) {
                 // survivors take their key (and, code points, their count) along: stage 2 needs nothing from the ring
-                if (go) sts128(q2_s + (q2n + __popc(surv & ((1u << lane) - 1u))) * kQ2Entry, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
+                if (go) {
+                    sts128(q2_s + (q2n + __popc(surv & ((1u << lane) - 1u))) * kQ2Entry, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
+                    // stage 2 will probe this slot a few windows from now: start the fetch
+                    const uint32_t x2 = klo + khi * kMixHi;
+                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(sv.ht + __umulhi(x2 * kMulSlot, sv.ht_size)));
+                }
                 q2n += __popc(surv);
             }
             // pop the round

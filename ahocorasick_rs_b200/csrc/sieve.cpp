@@ -247,6 +247,10 @@ uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_
         if (slot.node != kSieveNoNode) {
             slot.first_kid = na[slot.node].first_kid;
             slot.meta = na[slot.node].meta;
+            if (((slot.meta >> 8) & 0x1ffu) == 1) {
+                slot.kid_first_kid = na[slot.first_kid].first_kid;
+                slot.kid_meta = na[slot.first_kid].meta;
+            }
         }
 
     // ---- image ------------------------------------------------------------------------------------------------

@@ -109,7 +109,7 @@ struct SieveSlot {
     uint32_t node;            // kSieveNoNode = empty
     uint32_t pad;
     uint32_t first_kid, meta; // copy of the node's SieveNodeA
-    uint32_t pad1, pad2;
+    uint32_t kid_first_kid, kid_meta;  // a node with exactly ONE child (the rule in large random pattern sets): that child's record too
 };
 
 // Reverse trie, nodes of depth >= W, children of a node contiguous and sorted by byte.

@@ -147,6 +147,8 @@ class SieveImage:
             if meta & TERMINAL:
                 best = v
             nk = (meta >> 8) & 0x1FF
+            if d == W and nk == 1:   # the slot's inline copy of the only child
+                assert (int(self.ht[s][6]), int(self.ht[s][7])) == (int(self.na[first][0]), int(self.na[first][1]))
             if nk == 0 or e - 1 - d < hs:
                 break
             b = text[e - 1 - d]
