@@ -37,7 +37,10 @@
 
 namespace acb {
 
-constexpr int kSieveWarps = 24;   // 768 threads: 85 registers per thread (with 32 warps the window loop rematerialised half its state)
+#ifndef ACB_SIEVE_WARPS
+#define ACB_SIEVE_WARPS 24
+#endif
+constexpr int kSieveWarps = ACB_SIEVE_WARPS;   // 768 threads: 85 registers per thread (with 32 warps the window loop rematerialised half its state)
 constexpr int kSieveThreads = kSieveWarps * 32;
 constexpr uint32_t kWin = 512;                       // bytes per warp window
 constexpr uint32_t kSlotText = 16 + kWin;            // one ring slot: 16 bytes of history, then the window,
@@ -284,21 +287,19 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 const uint32_t x = klo + khi * kMixHi;
                 uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
                 uint32_t v = kSieveNoNode;
-                uint2 na = make_uint2(0, 0), only_kid = make_uint2(0, 0);
                 for (;;) {
                     const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
                     if (ent.z == kSieveNoNode) break;
                     if (ent.x == klo && ent.y == khi) {
                         v = ent.z;
-                        const uint4 rec = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s) + 1);  // same sector: the node's walk record
-                        na = make_uint2(rec.x, rec.y);
-                        only_kid = make_uint2(rec.z, rec.w);
                         break;
                     }
                     s = (s + 1) & (sv.ht_size - 1);
                 }
                 // walk towards the pattern start: node v = the d bytes that end at rel
                 uint32_t d = W;
+                uint2 na = make_uint2(0, 0);
+                if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
                 while (v != kSieveNoNode) {
                     if (na.y & kNodeTerminal) best = v;
                     const uint32_t nk = (na.y >> 8) & 0x1ffu;
@@ -306,13 +307,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                     const uint32_t b = __ldg(tptr + ((int64_t)(int32_t)rel - (int64_t)d));
                     uint32_t c = kSieveNoNode;
                     uint2 nc = make_uint2(0, 0);
-                    if (d == W && nk == 1) {
-                        // the slot brought the only child along: no access at all when the byte does not continue the pattern
-                        if ((only_kid.y & 0xffu) == b) {
-                            c = na.x;
-                            nc = only_kid;
-                        }
-                    } else if (nk <= 8) {
+                    if (nk <= 8) {
                         for (uint32_t t = 0; t < nk; t++) {
                             const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
                             const uint32_t cb = cand.y & 0xffu;
@@ -418,12 +413,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             const uint32_t surv = __ballot_sync(0xffffffffu, go);
             if (surv) {
                 // survivors take their key (and, code points, their count) along: stage 2 needs nothing from the ring
-                if (go) {
-                    sts128(q2_s + (q2n + __popc(surv & ((1u << lane) - 1u))) * kQ2Entry, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
-                    // stage 2 will probe this slot a few windows from now: start the fetch
-                    const uint32_t x2 = klo + khi * kMixHi;
-                    asm volatile("prefetch.global.L2 [%0];\n" ::"l"(sv.ht + __umulhi(x2 * kMulSlot, sv.ht_size)));
-                }
+                if (go) sts128(q2_s + (q2n + __popc(surv & ((1u << lane) - 1u))) * kQ2Entry, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
                 q2n += __popc(surv);
             }
             // pop the round

@@ -209,13 +209,13 @@ uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_
     // ---- hash table: window -> root node ------------------------------------------------------------
     uint32_t ht_size = 16;
     while (ht_size < 2 * uint64_t(n_keys)) ht_size <<= 1;
-    std::vector<SieveSlot> ht(ht_size, SieveSlot{0, 0, kSieveNoNode, 0, 0, 0, 0, 0});
+    std::vector<SieveSlot> ht(ht_size, SieveSlot{0, 0, kSieveNoNode, 0});
     for (uint32_t r = 0; r < n_keys; r++) {
         const uint32_t lo = (uint32_t)root_key[r], hi = (uint32_t)(root_key[r] >> 32);
         const uint32_t x = nodes[order[r]].x;
         uint32_t s = sieve_mulhi(x * kMulSlot, ht_size);
         while (ht[s].node != kSieveNoNode) s = (s + 1) & (ht_size - 1);
-        ht[s] = SieveSlot{lo, hi, r, 0, 0, 0, 0, 0};  // (the node's walk record is filled in below)
+        ht[s] = SieveSlot{lo, hi, r, 0};
     }
 
     // ---- nodes ------------------------------------------------------------------------------------------
@@ -243,16 +243,6 @@ uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_
         nb[v] = b;
     }
 
-    for (auto &slot : ht)
-        if (slot.node != kSieveNoNode) {
-            slot.first_kid = na[slot.node].first_kid;
-            slot.meta = na[slot.node].meta;
-            if (((slot.meta >> 8) & 0x1ffu) == 1) {
-                slot.kid_first_kid = na[slot.first_kid].first_kid;
-                slot.kid_meta = na[slot.first_kid].meta;
-            }
-        }
-
     // ---- image ------------------------------------------------------------------------------------------------
     SieveHeader h{};
     h.magic = kSieveMagic;
@@ -273,7 +263,6 @@ uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_
     uint64_t off = align16(sizeof(SieveHeader));
     h.off_bloom = off;
     off = align16(off + uint64_t(bloom_words) * 4);
-    off = (off + 31) & ~uint64_t(31);  // a slot is one 32-byte sector
     h.off_ht = off;
     off = align16(off + uint64_t(ht_size) * sizeof(SieveSlot));
     h.off_node_a = off;

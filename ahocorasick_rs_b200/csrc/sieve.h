@@ -102,14 +102,11 @@ struct SieveHeader {
     uint64_t total_bytes;
 };
 
-// hash table: W-byte suffix -> reverse-trie node of depth W.  One 32-byte sector per slot: the node's walk record
-// rides along, so a hit costs ONE dependent access before the children are looked at.
+// hash table: W-byte suffix -> reverse-trie node of depth W
 struct SieveSlot {
     uint32_t key_lo, key_hi;  // the window's bytes (as sieve_x sees them: lo', hi'), exact
     uint32_t node;            // kSieveNoNode = empty
     uint32_t pad;
-    uint32_t first_kid, meta; // copy of the node's SieveNodeA
-    uint32_t kid_first_kid, kid_meta;  // a node with exactly ONE child (the rule in large random pattern sets): that child's record too
 };
 
 // Reverse trie, nodes of depth >= W, children of a node contiguous and sorted by byte.

@@ -475,6 +475,7 @@ def main():
     rec_bytes = 24 if cfg == 4 else 16
     alg_bytes = bytes_per_step + 8 * (n_hay + 1) + rec_bytes * matches_per_step
     k_ms = kms.value / max(args.steps, 1)      # scan kernel time per step (a step above 2 GiB is several launches)
+    lps = max(kn.value / max(args.steps, 1), 1.0)   # scan kernel launches per step
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     engine = scan_stats.get("engine")
     kernel_name = "sieve_scan_kernel" if engine == "sieve" else ("scan_global_kernel" if scan_stats.get("global_table") else "scan_staged_kernel")
@@ -496,7 +497,8 @@ def main():
         "matches_per_step_per_gpu": matches_per_step,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": kernel_name,
-                     "kernel_ms": k_ms, "kernel_launches_per_step": kn.value / max(args.steps, 1), "algorithmic_bytes_per_launch": alg_bytes},
+                     "kernel_ms": k_ms / lps, "kernel_ms_per_step": k_ms, "kernel_launches_per_step": lps,
+                     "algorithmic_bytes_per_launch": alg_bytes / lps},
         "e2e": {"value": e2e_bytes * e2e_steps * world / e2e_s / 1e9, "unit": "GB/s",
                 "h2d_bytes_per_step": e2e_bytes + 8 * (len(e2e_in[0][1])), "d2h_bytes_per_step": d2h // e2e_steps,
                 "steps": e2e_steps, "bytes_per_step": e2e_bytes,

@@ -52,7 +52,7 @@ class SieveImage:
          self.max_pat_len, self.min_pat_len, self.n_keys, self.n_entries, self.prim_words, self.term_levels, _p1, _p2, o_bloom, o_ht, o_na, o_nb, o_pids, total) = f
         assert magic == 0x32424341 and total == n
         self.bloom = buf[o_bloom:o_bloom + 4 * self.bloom_words].view(np.uint32)
-        self.ht = buf[o_ht:o_ht + 32 * (self.ht_mask + 1)].view(np.uint32).reshape(-1, 8)
+        self.ht = buf[o_ht:o_ht + 16 * (self.ht_mask + 1)].view(np.uint32).reshape(-1, 4)
         nn = max(self.n_nodes, 1)
         self.na = buf[o_na:o_na + 8 * nn].view(np.uint32).reshape(-1, 2)
         self.nb = buf[o_nb:o_nb + 32 * nn].view(np.uint32).reshape(-1, 8)
@@ -140,15 +140,11 @@ class SieveImage:
                 break
             s = (s + 1) & self.ht_mask
         best, d = NO_NODE, W
-        if v != NO_NODE:
-            assert (int(self.ht[s][4]), int(self.ht[s][5])) == (int(self.na[v][0]), int(self.na[v][1])), "slot's copy of the node record"
         while v != NO_NODE:
             first, meta = int(self.na[v][0]), int(self.na[v][1])
             if meta & TERMINAL:
                 best = v
             nk = (meta >> 8) & 0x1FF
-            if d == W and nk == 1:   # the slot's inline copy of the only child
-                assert (int(self.ht[s][6]), int(self.ht[s][7])) == (int(self.na[first][0]), int(self.na[first][1]))
             if nk == 0 or e - 1 - d < hs:
                 break
             b = text[e - 1 - d]
