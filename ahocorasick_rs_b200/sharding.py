@@ -75,14 +75,15 @@ class MatchListGather:
     then its first `cap` matches -- to ONE all_gather per call.  On a GPU the block
     is assembled by one kernel of the library (acb_pack_gather_block) and the
     exchange runs on a side stream: the caller's stream never waits for the
-    collective of the step it just enqueued.  The caller alternates `slot` (and the
-    scan's workspace: scan_device(..., ws_slot=slot)) between 0 and 1; the scan that
-    reuses a slot's workspace two steps later is made to wait for that slot's
-    exchange -- long finished by then.  Call finish() before reading the result or
+    collective of the step it just enqueued.  The caller cycles `slot` (and the
+    scan's workspace: scan_device(..., ws_slot=slot)) through 0 .. slots-1; the scan that
+    reuses a slot's workspace `slots` steps later is made to wait for that slot's
+    exchange -- long finished by then (with eight ranks the collective's latency plus the
+    skew between ranks exceeds one 0.2 ms step: four slots keep the scans running).  Call finish() before reading the result or
     timing the stream.  decode_gathered() turns a result into the ordered global
     list (that is where the host finally looks at the counts)."""
 
-    def __init__(self, cap: int, device, group=None):
+    def __init__(self, cap: int, device, group=None, slots: int = 2):
         import torch
         import torch.distributed as dist
 
@@ -91,10 +92,11 @@ class MatchListGather:
         self.world = dist.get_world_size(group)
         self.device = device
         self.cuda = device.type == "cuda"
-        self.blocks = [torch.zeros((cap + 1, 4), dtype=torch.int32, device=device) for _ in range(2)]
-        self.everything = [torch.empty(self.world * (cap + 1) * 4, dtype=torch.int32, device=device) for _ in range(2)]
+        self.slots = slots   # exchanges that may be in flight: the scan that reuses a slot waits for that slot's exchange
+        self.blocks = [torch.zeros((cap + 1, 4), dtype=torch.int32, device=device) for _ in range(slots)]
+        self.everything = [torch.empty(self.world * (cap + 1) * 4, dtype=torch.int32, device=device) for _ in range(slots)]
         self.side = torch.cuda.Stream(device=device) if self.cuda else None
-        self.done = [None, None]
+        self.done = [None] * slots
 
     def __call__(self, matches, status, hay_base: int, slot: int = 0):
         """matches: the (capacity, 4) int32 output buffer of scan_device(sync=False); status: its
@@ -128,10 +130,10 @@ class MatchListGather:
             ev = torch.cuda.Event()
             ev.record(self.side)
             self.done[slot] = ev
-        # the next scan writes the OTHER slot's workspace, which the previous call's exchange read
-        other = self.done[1 - slot]
-        if other is not None:
-            main.wait_event(other)
+        # the NEXT scan writes the next slot's workspace, which the exchange `slots - 1` calls ago read
+        nxt = self.done[(slot + 1) % self.slots]
+        if nxt is not None:
+            main.wait_event(nxt)
         return everything.view(self.world, self.cap + 1, 4)
 
     def finish(self):

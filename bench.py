@@ -322,11 +322,13 @@ def main():
     cap = max(1 << 16, int(max(totals) * 1.25) + 1024)
     scan_stats = dict(ac._ac.last_stats)
 
+    SLOTS = 4   # workspaces / exchanges in flight (multi-GPU: the gather of step i overlaps the scans of steps i+1 .. i+3)
+
     def step(i):
         d, o = d_batches[i % len(d_batches)]
         if big:
             return ac.scan_device(d, o, ovl)                         # windows / runs of whole haystacks, synchronous
-        return ac.scan_device(d, o, ovl, capacity=cap, sync=False, ws_slot=i & 1)
+        return ac.scan_device(d, o, ovl, capacity=cap, sync=False, ws_slot=i % SLOTS)
 
     # ---- device-resident throughput ------------------------------------------------
     for i in range(args.warmup):
@@ -335,10 +337,10 @@ def main():
     gather = None
     if world > 1 and not big:
         gather_cap = max(4096, -(-2 * max(totals) // 4096) * 4096)  # rows per rank in the match-list gather
-        gather = MatchListGather(gather_cap, dev)
+        gather = MatchListGather(gather_cap, dev, slots=SLOTS)
         for i in range(max(args.warmup, 10)):  # warm the exchange too (communicator set-up, buffers)
             o_, _, t_ = step(i)
-            gather(o_, t_, (rank * 2 + (i & 1)) * n_hay, slot=i & 1)
+            gather(o_, t_, (rank * 2 + (i & 1)) * n_hay, slot=i % SLOTS)
         gather.finish()
     if world > 1:
         dist.barrier()
@@ -356,9 +358,10 @@ def main():
         if world > 1:
             # the only exchange of the path: gather the per-shard match lists
             if gather is not None:
-                gathered = gather(out, tot, (rank * 2 + (i & 1)) * n_hay, slot=i & 1)   # fixed-size blocks, side stream, no host round trip
+                gathered = gather(out, tot, (rank * 2 + (i & 1)) * n_hay, slot=i % SLOTS)   # fixed-size blocks, side stream, no host round trip
             else:
-                gathered = gather_match_lists(out, rank * n_hay)   # exact sizes, two collectives (the lists are tens of MB here)
+                rows = out.to(torch.int32) if (out.dtype != torch.int32 and bytes_per_step // max(n_hay, 1) < (1 << 31) and n_hay * world < (1 << 31)) else out
+                gathered = gather_match_lists(rows, rank * n_hay)   # exact sizes, two collectives (the lists are tens of MB here)
     if gather is not None:
         gather.finish()  # the exchanges ran on a side stream: the timed region ends when the last one has
     ev1.record()
