@@ -47,16 +47,11 @@ constexpr uint32_t kSlotText = 16 + kWin;            // one ring slot: 16 bytes 
 constexpr uint32_t kSlotBytes = kSlotText + 48;      // then (code points) continuation bytes per 16-byte chunk (32 x u8) and before the window (u32)
 constexpr uint32_t kQueueCap = 64;                   // positions per queue (a round takes 32; at most 32 arrive at a time)
 constexpr uint32_t kRingMax = 8;
-constexpr uint32_t kQ2Entry = 32;                    // second queue: position, key (2 words), code point count | haystack, its start
-constexpr int kSieveConsumers = kSieveWarps / 4;     // warps that only verify (stage 2); the others scan (fast path + stage 1)
-constexpr int kSieveProducers = kSieveWarps - kSieveConsumers;
-constexpr int kServe = kSieveProducers / kSieveConsumers;  // producers per consumer
-static_assert(kSieveProducers % kSieveConsumers == 0, "every consumer serves the same number of producers");
-constexpr uint32_t kMarkBegin = 0xffffffffu, kMarkEnd = 0xfffffffeu, kMarkDone = 0xfffffffdu;  // in-band messages of the second queue
-// per PRODUCER warp: ring | pad | first queue (positions) | second queue (a ring shared with its consumer) | queue control | consumer state
-__host__ __device__ constexpr uint32_t sieve_warp_bytes(uint32_t ring, bool cp) { return ring * kSlotBytes + 16 + kQueueCap * 4u + kQueueCap * kQ2Entry + 64; }
+constexpr uint32_t kQ2Entry = 16;                    // second queue: position, key (2 words), code point count
+// per warp: ring | pad | first queue (positions) | second queue
+__host__ __device__ constexpr uint32_t sieve_warp_bytes(uint32_t ring, bool cp) { return ring * kSlotBytes + 16 + kQueueCap * 4u + kQueueCap * kQ2Entry; }
 __host__ __device__ constexpr uint32_t sieve_smem_bytes(uint32_t filter_bytes, uint32_t ring, bool cp) {
-    return filter_bytes + 16 + kSieveProducers * sieve_warp_bytes(ring, cp);
+    return filter_bytes + 16 + kSieveWarps * sieve_warp_bytes(ring, cp);
 }
 
 struct DevSieve {
@@ -154,13 +149,8 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         mbar_expect_tx(bar_s, bloom_bytes);
         tma_bulk_g2s(bloom_s, sv.bloom, bloom_bytes, bar_s);
     }
-    const uint32_t q2ctl_s = q2_s + kQueueCap * kQ2Entry;  // +0: entries ever queued (producer), +4: entries consumed (consumer); +32: the consumer's state
-    const bool producer = warp < (uint32_t)kSieveProducers;
-    if (producer) {
-        // the pad behind the ring stays zero (a key read may touch one aligned word past the last slot); so do the queue's counters
-        if (lane < 4) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(ring_s + R * kSlotBytes + lane * 4), "r"(0u) : "memory");
-        if (lane < 16) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(q2ctl_s + lane * 4), "r"(0u) : "memory");
-    }
+    // the pad behind the ring stays zero (a key read may touch one aligned word past the last slot)
+    if (lane < 4) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(ring_s + R * kSlotBytes + lane * 4), "r"(0u) : "memory");
     __syncthreads();
     mbar_wait(bar_s, 0);
 
@@ -203,192 +193,6 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         return n + cont_prefix(sl + 16 + 16 * L, k + 1);
     };
 
-
-    // =====================================================================================================================
-    // Consumer warps: stage 2 only.  Each serves kServe producers through their second queues (rings in shared memory
-    // with in-band messages: task begin / task end / done).  A round = up to 32 positions of ONE producer's current task,
-    // in queue order, so the ranks of a task's matches are handed out in stream order by exactly one warp.
-    // =====================================================================================================================
-    if (!producer) {
-        const uint32_t cid = warp - kSieveProducers;
-        uint32_t alive = kServe;
-        while (alive) {
-            bool progressed = false;
-#pragma unroll 1
-            for (uint32_t j = 0; j < (uint32_t)kServe; j++) {
-                const uint32_t pbase = bar_s + 16 + (cid * kServe + j) * sieve_warp_bytes(R, CP);
-                const uint32_t pq2 = pbase + R * kSlotBytes + 16 + kQueueCap * 4u, pctl = pq2 + kQueueCap * kQ2Entry, pst = pctl + 32;
-                // consumer state of this producer: +0 t_lo (i64), +8 task, +12 matches of the task so far, +16 head, +20 done
-                if (lds32v(pst + 20)) continue;
-                uint32_t head = lds32v(pst + 16), tail;
-                asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(tail) : "r"(pctl) : "memory");
-                const uint32_t avail = tail - head;
-                if (avail == 0) continue;
-                __threadfence_block();
-                const uint32_t n = min(avail, 32u);
-                uint4 e0 = make_uint4(0, 0, 0, 0), e1 = make_uint4(0, 0, 0, 0);
-                if (lane < n) {
-                    const uint32_t a = pq2 + ((head + lane) & (kQueueCap - 1)) * kQ2Entry;
-                    e0 = lds128(a);
-                    e1 = lds128(a + 16);
-                }
-                const uint32_t marks = __ballot_sync(0xffffffffu, lane < n && e0.x >= kMarkDone);
-                if (!marks && n < 32) continue;  // wait for a full round, or for a message that closes a shorter one
-                const uint32_t m = marks ? (uint32_t)__ffs(marks) - 1u : n;
-                progressed = true;
-                if (m == 0) {
-                    // a message from the producer
-                    const uint32_t kind = __shfl_sync(0xffffffffu, e0.x, 0);
-                    if (lane == 0) {
-                        if (kind == kMarkBegin) {
-                            asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};\n" ::"r"(pst), "r"(e0.z), "r"(e0.w), "r"(e0.y), "r"(0u) : "memory");
-                        } else if (kind == kMarkEnd) {
-                            out.unit_counts[lds32v(pst + 8)] = lds32v(pst + 12);
-                        } else {
-                            asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(pst + 20), "r"(1u) : "memory");
-                        }
-                    }
-                    if (kind == kMarkDone) alive--;
-                    head += 1;
-                } else {
-                    const bool active = lane < m;
-                    const uint32_t rel = e0.x, klo = e0.y, khi = e0.z, aux = e0.w;
-                    const int64_t h = (int64_t)e1.x;
-                    const int32_t hs = (int32_t)e1.y;
-                    const uint2 tl = lds64(pst);
-                    const uint8_t *tptr = B.bytes + (int64_t)(((uint64_t)tl.y << 32) | tl.x);
-                    const uint32_t task = lds32v(pst + 8), n_emitted = lds32v(pst + 12);
-                    uint32_t best = kSieveNoNode, cnt = 0;
-                    if (active && (int32_t)rel - (int32_t)(sv.W - 1) >= hs) {
-                        const uint32_t x = klo + khi * kMixHi;
-                        uint32_t sl = __umulhi(x * kMulSlot, sv.ht_size);
-                        uint32_t v = kSieveNoNode;
-                        for (;;) {
-                            const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + sl));
-                            if (ent.z == kSieveNoNode) break;
-                            if (ent.x == klo && ent.y == khi) {
-                                v = ent.z;
-                                break;
-                            }
-                            sl = (sl + 1) & (sv.ht_size - 1);
-                        }
-                        // walk towards the pattern start: node v = the d bytes that end at rel
-                        uint32_t d = sv.W;
-                        uint2 na = make_uint2(0, 0);
-                        if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
-                        while (v != kSieveNoNode) {
-                            if (na.y & kNodeTerminal) best = v;
-                            const uint32_t nk = (na.y >> 8) & 0x1ffu;
-                            if (nk == 0 || (int32_t)rel - (int32_t)d < hs) break;  // no longer pattern, or it would start before the haystack
-                            const uint32_t b = __ldg(tptr + ((int64_t)(int32_t)rel - (int64_t)d));
-                            uint32_t c = kSieveNoNode;
-                            uint2 nc = make_uint2(0, 0);
-                            if (nk <= 8) {
-                                for (uint32_t t = 0; t < nk; t++) {
-                                    const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
-                                    const uint32_t cb = cand.y & 0xffu;
-                                    if (cb >= b) {
-                                        if (cb == b) {
-                                            c = na.x + t;
-                                            nc = cand;
-                                        }
-                                        break;
-                                    }
-                                }
-                            } else {
-                                uint32_t l0 = 0, l1 = nk;  // first child with byte >= b
-                                while (l0 < l1) {
-                                    const uint32_t mid = (l0 + l1) >> 1;
-                                    if ((__ldg(&sv.na[na.x + mid].meta) & 0xffu) < b)
-                                        l0 = mid + 1;
-                                    else
-                                        l1 = mid;
-                                }
-                                if (l0 < nk) {
-                                    const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + l0));
-                                    if ((cand.y & 0xffu) == b) {
-                                        c = na.x + l0;
-                                        nc = cand;
-                                    }
-                                }
-                            }
-                            v = c;
-                            na = nc;
-                            d++;
-                        }
-                        if (best != kSieveNoNode) cnt = __ldg(&sv.nb[best].chain_cnt);
-                    }
-                    const uint32_t hits = __ballot_sync(0xffffffffu, cnt != 0);
-                    if (hits) {
-                        uint32_t total;
-                        const uint32_t exc = warp_excl_scan(cnt, lane, &total);
-                        unsigned long long rbase = 0;
-                        if (lane == 0) rbase = atomicAdd(out.raw_total, (unsigned long long)total);
-                        rbase = __shfl_sync(0xffffffffu, rbase, 0);
-                        if (cnt) {
-                            unsigned long long idx = rbase + exc;
-                            uint32_t seq = n_emitted + exc;
-                            const uint32_t end_rel = (uint32_t)((int32_t)rel + 1 - hs);
-                            for (uint32_t u = best; u != kSieveNoNode;) {
-                                const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(sv.nb + u));  // own_off, own_cnt, term_link, depth
-                                for (uint32_t t = 0; t < nb.y; t++, idx++, seq++) {
-                                    if (idx < out.cap) {
-                                        const uint32_t pid = __ldg(sv.pids + nb.x + t);
-                                        reinterpret_cast<uint4 *>(out.raw)[idx] = make_uint4((uint32_t)h, pid, end_rel - nb.w, end_rel);
-                                        out.raw_seq[idx] = seq;
-                                        out.raw_unit[idx] = task;
-                                        if (CP) out.raw_aux[idx] = aux;
-                                    }
-                                }
-                                u = nb.z;
-                            }
-                        }
-                        if (lane == 0) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(pst + 12), "r"(n_emitted + total) : "memory");
-                    }
-                    head += m;
-                }
-                if (lane == 0) {
-                    asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(pst + 16), "r"(head) : "memory");
-                    __threadfence_block();
-                    asm volatile("st.volatile.shared.u32 [%0], %1;\n" ::"r"(pctl + 4), "r"(head) : "memory");  // room for the producer
-                }
-                __syncwarp();
-            }
-            if (!progressed) __nanosleep(200);
-        }
-        return;
-    }
-
-    // =====================================================================================================================
-    // Producer warps: the scan proper (fast path, queueing, stage 1)
-    // =====================================================================================================================
-    uint32_t q2_tail = 0;  // entries this warp has ever put into its second queue
-    // make room for cnt (<= 32) more entries in the second queue: wait for the consumer
-    auto q2_room = [&](uint32_t cnt) {
-        if (lane == 0) {
-            for (;;) {
-                uint32_t head;
-                asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(head) : "r"(q2ctl_s + 4) : "memory");
-                if (q2_tail + cnt - head <= kQueueCap) break;
-                __nanosleep(100);
-            }
-        }
-        __syncwarp();
-    };
-    auto q2_publish = [&](uint32_t cnt) {
-        __syncwarp();
-        q2_tail += cnt;
-        if (lane == 0) {
-            __threadfence_block();
-            asm volatile("st.volatile.shared.u32 [%0], %1;\n" ::"r"(q2ctl_s), "r"(q2_tail) : "memory");
-        }
-    };
-    auto q2_message = [&](uint32_t kind, uint32_t a, uint32_t b, uint32_t c) {
-        q2_room(1);
-        if (lane == 0) sts128(q2_s + (q2_tail & (kQueueCap - 1)) * kQ2Entry, make_uint4(kind, a, b, c));
-        q2_publish(1);
-    };
-
     unsigned int claimed = 0;
     if (lane == 0) claimed = atomicAdd(task_counter, 1u);
     for (;;) {
@@ -403,7 +207,6 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             }
             continue;
         }
-        q2_message(kMarkBegin, task, (uint32_t)(uint64_t)t_lo, (uint32_t)((uint64_t)t_lo >> 32));
         // the task's part of the stream, [lo_r, hi_r) relative to t_lo; positions (= index of a window's LAST byte) from
         // plo_r on can end a match: the W-byte window must lie inside the stream
         const uint32_t lo_r = (uint32_t)max(vlo - t_lo, (int64_t)0), hi_r = (uint32_t)min(vhi - t_lo, (int64_t)T);
@@ -464,13 +267,121 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             return h;
         };
 
-        uint32_t q1n = 0;
+        uint32_t n_emitted = 0, q1n = 0, q2n = 0;
         uint32_t q1_head = 0;  // window index of the first queue's first entry (valid while the queue is not empty)
         uint32_t cp_before = 0;             // code points: continuation bytes of the task before the current window
         uint32_t wrel = wfirst;
 
+        // ---- stage 2: exact verification of the first (up to) 32 positions of the second queue ----
+        auto round2 = [&]() {
+            const uint32_t n = min(q2n, 32u);
+            const bool active = lane < n;
+            uint4 ent2 = make_uint4(0, 0, 0, 0);  // position, key (2 words), continuation bytes before the end
+            if (active) ent2 = lds128(q2_s + lane * kQ2Entry);
+            const uint32_t rel = ent2.x, aux = ent2.w;
+            int32_t hs;
+            const int64_t h = hay_of(active ? rel : max(wrel, lo_r), hs);
+            uint32_t best = kSieveNoNode, cnt = 0;
+            if (active && (int32_t)rel - (int32_t)(W - 1) >= hs) {
+                const uint32_t klo = ent2.y, khi = ent2.z;
+                const uint32_t x = klo + khi * kMixHi;
+                uint32_t s = __umulhi(x * kMulSlot, sv.ht_size);
+                uint32_t v = kSieveNoNode;
+                for (;;) {
+                    const uint4 ent = __ldg(reinterpret_cast<const uint4 *>(sv.ht + s));
+                    if (ent.z == kSieveNoNode) break;
+                    if (ent.x == klo && ent.y == khi) {
+                        v = ent.z;
+                        break;
+                    }
+                    s = (s + 1) & (sv.ht_size - 1);
+                }
+                // walk towards the pattern start: node v = the d bytes that end at rel
+                uint32_t d = W;
+                uint2 na = make_uint2(0, 0);
+                if (v != kSieveNoNode) na = __ldg(reinterpret_cast<const uint2 *>(sv.na + v));
+                while (v != kSieveNoNode) {
+                    if (na.y & kNodeTerminal) best = v;
+                    const uint32_t nk = (na.y >> 8) & 0x1ffu;
+                    if (nk == 0 || (int32_t)rel - (int32_t)d < hs) break;  // no longer pattern, or it would start before the haystack
+                    const uint32_t b = __ldg(tptr + ((int64_t)(int32_t)rel - (int64_t)d));
+                    uint32_t c = kSieveNoNode;
+                    uint2 nc = make_uint2(0, 0);
+                    if (nk <= 8) {
+                        for (uint32_t t = 0; t < nk; t++) {
+                            const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + t));
+                            const uint32_t cb = cand.y & 0xffu;
+                            if (cb >= b) {
+                                if (cb == b) {
+                                    c = na.x + t;
+                                    nc = cand;
+                                }
+                                break;
+                            }
+                        }
+                    } else {
+                        uint32_t l0 = 0, l1 = nk;  // first child with byte >= b
+                        while (l0 < l1) {
+                            const uint32_t mid = (l0 + l1) >> 1;
+                            if ((__ldg(&sv.na[na.x + mid].meta) & 0xffu) < b)
+                                l0 = mid + 1;
+                            else
+                                l1 = mid;
+                        }
+                        if (l0 < nk) {
+                            const uint2 cand = __ldg(reinterpret_cast<const uint2 *>(sv.na + na.x + l0));
+                            if ((cand.y & 0xffu) == b) {
+                                c = na.x + l0;
+                                nc = cand;
+                            }
+                        }
+                    }
+                    v = c;
+                    na = nc;
+                    d++;
+                }
+                if (best != kSieveNoNode) cnt = __ldg(&sv.nb[best].chain_cnt);
+            }
+            const uint32_t hits = __ballot_sync(0xffffffffu, cnt != 0);
+            if (hits) {
+                uint32_t total;
+                const uint32_t exc = warp_excl_scan(cnt, lane, &total);
+                unsigned long long rbase = 0;
+                if (lane == 0) rbase = atomicAdd(out.raw_total, (unsigned long long)total);
+                rbase = __shfl_sync(0xffffffffu, rbase, 0);
+                if (cnt) {
+                    unsigned long long idx = rbase + exc;
+                    uint32_t seq = n_emitted + exc;
+                    const uint32_t end_rel = (uint32_t)((int32_t)rel + 1 - hs);
+                    for (uint32_t u = best; u != kSieveNoNode;) {
+                        const uint4 nb = __ldg(reinterpret_cast<const uint4 *>(sv.nb + u));  // own_off, own_cnt, term_link, depth
+                        for (uint32_t t = 0; t < nb.y; t++, idx++, seq++) {
+                            if (idx < out.cap) {
+                                const uint32_t pid = __ldg(sv.pids + nb.x + t);
+                                reinterpret_cast<uint4 *>(out.raw)[idx] = make_uint4((uint32_t)h, pid, end_rel - nb.w, end_rel);
+                                out.raw_seq[idx] = seq;
+                                out.raw_unit[idx] = task;
+                                if (CP) out.raw_aux[idx] = aux;
+                            }
+                        }
+                        u = nb.z;
+                    }
+                }
+                n_emitted += total;
+            }
+            // pop the round
+            uint4 keep = make_uint4(0, 0, 0, 0);
+            const bool mv = 32 + lane < q2n;
+            if (mv) keep = lds128(q2_s + (32 + lane) * kQ2Entry);
+            __syncwarp();
+            if (mv) sts128(q2_s + lane * kQ2Entry, keep);
+            q2n -= n;
+            __syncwarp();
+        };
+
         // ---- stage 1: second filter and the on-chip walk for the first (up to) 32 positions of the first queue ----
         auto round1 = [&]() {
+            if (q2n > 32) round2();  // room for 32 survivors
             const uint32_t n = min(q1n, 32u);
             const bool active = lane < n;
             uint32_t rel = 0, klo = 0, khi = 0;
@@ -501,18 +412,9 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             }
             const uint32_t surv = __ballot_sync(0xffffffffu, go);
             if (surv) {
-                // survivors go to the consumer warp with everything stage 2 needs: key, haystack and its start (and, code
-                // points, their count): nothing of this warp's ring or registers is touched again for them
-                int32_t hs;
-                const int64_t h = hay_of(go ? rel : max(wrel, lo_r), hs);
-                const uint32_t cnt = __popc(surv);
-                q2_room(cnt);
-                if (go) {
-                    const uint32_t a = q2_s + ((q2_tail + __popc(surv & ((1u << lane) - 1u))) & (kQueueCap - 1)) * kQ2Entry;
-                    sts128(a, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
-                    sts128(a + 16, make_uint4((uint32_t)h, (uint32_t)hs, 0u, 0u));
-                }
-                q2_publish(cnt);
+                // survivors take their key (and, code points, their count) along: stage 2 needs nothing from the ring
+                if (go) sts128(q2_s + (q2n + __popc(surv & ((1u << lane) - 1u))) * kQ2Entry, make_uint4(rel, klo, khi, CP ? cont_upto_end(rel) : 0u));
+                q2n += __popc(surv);
             }
             // pop the round
             uint32_t keep = 0;
@@ -678,11 +580,11 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             nx1 = nx2;
         }
         while (q1n) round1();
-        q2_message(kMarkEnd, task, 0u, 0u);   // the consumer writes the task's match count when it gets here
+        while (q2n) round2();
+        if (lane == 0) out.unit_counts[task] = n_emitted;
         if (CP && lane == 0) task_cont[task] = cp_before;
         __syncwarp();
     }
-    q2_message(kMarkDone, 0u, 0u, 0u);
 }
 
 }  // namespace acb

@@ -165,7 +165,7 @@ class _Automaton:
     # ---- the sieve image (position-parallel scan: Bloom filter in shared memory + reverse trie in HBM/L2) ----
     ENGINE = __import__("os").environ.get("ACB200_ENGINE", "auto")   # "auto" | "sieve" | "table": kernel family (see scan_device)
     AUTO_PROFILE_BYTES = 4 << 20     # "auto": inputs below this never pay for the profiling pass
-    SIEVE_SMEM_RESERVE = int(__import__("os").environ.get("ACB200_SIEVE_RESERVE_KB", "54")) * 1024   # 18 scanning warps x (one ring slot of text + two queues + control); barrier
+    SIEVE_SMEM_RESERVE = int(__import__("os").environ.get("ACB200_SIEVE_RESERVE_KB", "46")) * 1024   # 24 warps x (one ring slot of text + two queues); barrier
     SIEVE_W_MAX = 0                  # 0 = the builder chooses the primary window
 
     def sieve(self, device):
