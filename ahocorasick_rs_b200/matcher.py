@@ -40,6 +40,9 @@ class Implementation(enum.Enum):
     DFA = 2
 
 
+_TRACE = bool(__import__("os").environ.get("ACB200_TRACE"))
+
+
 def _torch():
     import torch
     return torch
@@ -438,13 +441,18 @@ class _Automaton:
                     h1 = h + int(big[0].item())
             end = int(offsets[h1].item())
             sub_offs = offsets[h:h1 + 1] - start
+            _t0 = __import__("time").perf_counter() if _TRACE else 0
             m, mo_run, total = self.scan_device(data[start:end], sub_offs, overlapping, codepoints)
+            _t1 = __import__("time").perf_counter() if _TRACE else 0
             part = m.to(torch.int64)
             if h:
                 part[:, 0] += h
             parts.append(part)
             mo[h + 1:h1 + 1] = mo_run[1:h1 - h + 1].to(torch.int64) + base_count
             base_count += int(total)
+            if _TRACE:
+                torch.cuda.synchronize()
+                print(f"[trace] run haystacks {h}..{h1} ({end - start} B): scan_device {(_t1 - _t0) * 1e3:.2f} ms, post {(__import__('time').perf_counter() - _t1) * 1e3:.2f} ms, total {total}", flush=True)
             h = h1
         out = torch.cat(parts, dim=0) if len(parts) != 1 else parts[0]
         if not parts:

@@ -6,4 +6,7 @@ timeout 600 python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > g
 for n in 2 4 8; do
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600+n)) bench.py --gpus $n --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r02_scale_c2_n$n.json 2> gpurun_out/s_err$n.txt; line gpurun_out/r02_scale_c2_n$n.json "c2 n$n" gpurun_out/s_err$n.txt
 done
-timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 bench.py --gpus 8 --config 5 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/r02_scale_c5_n8.json 2> gpurun_out/s_err58.txt; line gpurun_out/r02_scale_c5_n8.json "c5 n8" gpurun_out/s_err58.txt
+NCCL_DEBUG=INFO timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29650 bench.py --gpus 8 --config 5 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/s_c5_n8.out 2> gpurun_out/s_err58.txt
+grep -v "NCCL INFO" gpurun_out/s_c5_n8.out | tail -1 > gpurun_out/r02_scale_c5_n8.json; line gpurun_out/r02_scale_c5_n8.json "c5 n8" gpurun_out/s_err58.txt
+grep -h "NCCL INFO" gpurun_out/s_c5_n8.out gpurun_out/s_err58.txt | grep -E "via|NVLS|Channel 00|Connected|Using network|P2P" | head -12 > gpurun_out/r02_nccl_transport.txt; cat gpurun_out/r02_nccl_transport.txt | cut -c1-200
+rm -f gpurun_out/s_c5_n8.out
