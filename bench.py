@@ -360,8 +360,12 @@ def main():
             if gather is not None:
                 gathered = gather(out, tot, (rank * 2 + (i & 1)) * n_hay, slot=i % SLOTS)   # fixed-size blocks, side stream, no host round trip
             else:
+                _g0 = time.perf_counter()
                 rows = out.to(torch.int32) if (out.dtype != torch.int32 and bytes_per_step // max(n_hay, 1) < (1 << 31) and n_hay * world < (1 << 31)) else out
                 gathered = gather_match_lists(rows, rank * n_hay)   # exact sizes, two collectives (the lists are tens of MB here)
+                if os.environ.get("ACB200_TRACE"):
+                    torch.cuda.synchronize()
+                    print(f"[trace] rank {rank} step {i}: gather {1e3 * (time.perf_counter() - _g0):.2f} ms for {rows.shape[0]} local rows", flush=True)
     if gather is not None:
         gather.finish()  # the exchanges ran on a side stream: the timed region ends when the last one has
     ev1.record()
