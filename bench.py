@@ -342,6 +342,14 @@ def main():
             o_, _, t_ = step(i)
             gather(o_, t_, (rank * 2 + (i & 1)) * n_hay, slot=i % SLOTS)
         gather.finish()
+    def big_gather(out):
+        rows = out.to(torch.int32) if (out.dtype != torch.int32 and bytes_per_step // max(n_hay, 1) < (1 << 31) and n_hay * world < (1 << 31)) else out
+        return gather_match_lists(rows, rank * n_hay)   # exact sizes, two collectives (the lists are tens of MB here)
+
+    if world > 1 and big:
+        for i in range(max(args.warmup, 3)):   # warm the exchange too: communicator set-up, the kept buffers, the allocator's blocks
+            gathered = big_gather(step(i)[0])
+        gathered = None
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -360,12 +368,7 @@ def main():
             if gather is not None:
                 gathered = gather(out, tot, (rank * 2 + (i & 1)) * n_hay, slot=i % SLOTS)   # fixed-size blocks, side stream, no host round trip
             else:
-                _g0 = time.perf_counter()
-                rows = out.to(torch.int32) if (out.dtype != torch.int32 and bytes_per_step // max(n_hay, 1) < (1 << 31) and n_hay * world < (1 << 31)) else out
-                gathered = gather_match_lists(rows, rank * n_hay)   # exact sizes, two collectives (the lists are tens of MB here)
-                if os.environ.get("ACB200_TRACE"):
-                    torch.cuda.synchronize()
-                    print(f"[trace] rank {rank} step {i}: gather {1e3 * (time.perf_counter() - _g0):.2f} ms for {rows.shape[0]} local rows", flush=True)
+                gathered = big_gather(out)
     if gather is not None:
         gather.finish()  # the exchanges ran on a side stream: the timed region ends when the last one has
     ev1.record()
