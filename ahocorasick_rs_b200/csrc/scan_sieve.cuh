@@ -45,6 +45,7 @@ constexpr int kSieveThreads = kSieveWarps * 32;
 constexpr uint32_t kWin = 512;                       // bytes per warp window
 constexpr uint32_t kSlotText = 16 + kWin;            // one ring slot: 16 bytes of history, then the window,
 constexpr uint32_t kSlotBytes = kSlotText + 48;      // then (code points) continuation bytes per 16-byte chunk (32 x u8) and before the window (u32)
+static_assert(kSieveWarps != 24 || (kSieveScanWarps == 24 && kSieveRingSlotBytes == kSlotBytes), "sieve.h: the builder's copy of the kernel geometry");
 constexpr uint32_t kQueueCap = 64;                   // positions per queue (a round takes 32; at most 32 arrive at a time)
 constexpr uint32_t kRingMax = 8;
 constexpr uint32_t kQ2Entry = 16;                    // second queue: position, key (2 words), code point count
@@ -137,8 +138,10 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
     const uint32_t bar_s = bloom_s + bloom_bytes;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t R = P.ring;  // a power of two
-    const uint32_t ring_s = bar_s + 16 + warp * sieve_warp_bytes(R, CP);
-    const uint32_t q1_s = ring_s + R * kSlotBytes + 16, q2_s = q1_s + kQueueCap * 4u;
+    uint32_t ring_s = bar_s + 16 + warp * sieve_warp_bytes(R, CP);
+    asm volatile("" : "+r"(ring_s));  // (kept in a register: left alone, the compiler recomputes it from the thread id at every use)
+    const uint32_t ring_end = ring_s + R * kSlotBytes;
+    const uint32_t q1_s = ring_end + 16, q2_s = q1_s + kQueueCap * 4u;
     const uint32_t n_words = sv.prim_words;              // the primary bitmap (fast path)
     const uint32_t sec_s = bloom_s + sv.prim_words * 4;  // the secondary filter
     const uint32_t sec_words = sv.bloom_words - sv.prim_words;
@@ -380,8 +383,7 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
         };
 
         // ---- stage 1: second filter and the on-chip walk for the first (up to) 32 positions of the first queue ----
-        auto round1 = [&]() {
-            if (q2n > 32) round2();  // room for 32 survivors
+        auto round1 = [&]() {  // (the caller has made room for 32 survivors in the second queue)
             const uint32_t n = min(q1n, 32u);
             const bool active = lane < n;
             uint32_t rel = 0, klo = 0, khi = 0;
@@ -435,16 +437,17 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
             if (lane == 0) sts128(text_s(wrel) - 16, c);
         }
         uint4 cur = load16(wrel + 16 * lane);
-        uint4 nx1 = make_uint4(0, 0, 0, 0), nx2 = make_uint4(0, 0, 0, 0);
-        if (wrel + kWin <= wlast) nx1 = load16(wrel + kWin + 16 * lane);
+        uint4 nxt = make_uint4(0, 0, 0, 0);
+        uint32_t cur_slot = slot_s(wrel);  // the ring slot of the current window
 
         for (;; wrel += kWin) {
-            if (wrel + 2 * kWin <= wlast) {
-                // two windows ahead: whole windows inside the stream (all but a task's edges) take the direct load
-                if (wrel + 2 * kWin >= lo_r && wrel + 3 * kWin <= hi_r)
-                    nx2 = __ldg(reinterpret_cast<const uint4 *>(tptr + (wrel + 2 * kWin + 16 * lane)));
+            if (wrel + kWin <= wlast) {
+                // the next window (a window takes a warp a few microseconds: one load in flight per lane covers the latency);
+                // whole windows inside the stream (all but a task's edges) take the direct load
+                if (wrel + kWin >= lo_r && wrel + 2 * kWin <= hi_r)
+                    nxt = __ldg(reinterpret_cast<const uint4 *>(tptr + (wrel + kWin + 16 * lane)));
                 else
-                    nx2 = load16(wrel + 2 * kWin + 16 * lane);
+                    nxt = load16(wrel + kWin + 16 * lane);
             }
             // ---- fast path: first filter probe for the 16 positions of this lane ----
             uint32_t pz = __shfl_up_sync(0xffffffffu, cur.z, 1), pw = __shfl_up_sync(0xffffffffu, cur.w, 1);
@@ -500,8 +503,9 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                 starts_inside = next_start < (int32_t)wend || __shfl_sync(0xffffffffu, offc, 0) >= (int32_t)max(wrel, lo_r);
             }
             const bool any = __any_sync(0xffffffffu, m1 != 0);
+            uint32_t tot1 = 0, ex1 = 0;  // survivors of the first probe in this window, and in the lanes before this one
             if (any || starts_inside) {
-                const uint32_t sl = slot_s(wrel);
+                const uint32_t sl = cur_slot;
                 sts128(sl + 16 + 16 * lane, cur);
                 if (CP) {
                     asm volatile("st.shared.u8 [%0], %1;\n" ::"r"(sl + kSlotText + lane), "r"(wc) : "memory");
@@ -530,57 +534,54 @@ sieve_scan_kernel(DevSieve sv, Batch B, SievePlan P, Sink out, uint32_t *task_co
                         next_start = __shfl_sync(0xffffffffu, offc, 1);
                     }
                 }
-                if (any) {
-                    // ---- queue this window's survivors, in stream order: a lane's go behind those of the lanes before it ----
-                    uint32_t tot1;
-                    const uint32_t ex1 = warp_excl_scan(__popc(m1), lane, &tot1);
-                    if (q1n + tot1 <= kQueueCap) {
-                        uint32_t at = q1n + ex1;
-                        for (uint32_t m = m1; m; m &= m - 1) q1_store(at++, wrel + 16 * lane + (__ffs(m) - 1));
-                        if (q1n == 0) q1_head = wrel >> 9;
-                        q1n += tot1;
-                        __syncwarp();
-                        while (q1n >= 32) round1();
-                    } else {
-                        // a window with more survivors than the queue takes at once: 32 at a time (lane i takes the (base + i)-th)
-                        for (uint32_t base = 0; base < tot1; base += 32) {
-                            const uint32_t g = base + lane;
-                            const bool active = g < tot1;
-                            uint32_t L = 0;
-#pragma unroll
-                            for (int step = 16; step >= 1; step >>= 1) {
-                                const uint32_t c = L + step;
-                                const uint32_t v = __shfl_sync(0xffffffffu, ex1, c & 31);
-                                if (c < 32 && v <= g) L = c;
-                            }
-                            const uint32_t mL = __shfl_sync(0xffffffffu, m1, L), exL = __shfl_sync(0xffffffffu, ex1, L);
-                            uint32_t k = 0;
-                            if (active) k = __fns(mL, 0, (int)(g - exL) + 1);
-                            if (active) q1_store(q1n + lane, wrel + 16 * L + k);
-                            if (q1n == 0) q1_head = wrel >> 9;
-                            q1n += min(tot1 - base, 32u);
-                            __syncwarp();
-                            while (q1n >= 32) round1();
-                        }
-                    }
-                }
+                if (any) ex1 = warp_excl_scan(__popc(m1), lane, &tot1);
             }
             if (CP && wany) cp_before += __reduce_add_sync(0xffffffffu, wc);
-            if (wrel >= wlast) break;
-            // what is still queued from the window whose ring slot the next window will take has to go now
+            // ---- queue this window's survivors, in stream order (a lane's go behind those of the lanes before it), and
+            // run the later stages: ONE instance of each in the code (they are large; four inlined copies of them cost more
+            // in instruction fetch than the calls they saved).  A window with more survivors than the first queue has room
+            // for is pushed in pieces.  Stage 1 runs when 32 positions wait, or when their text is about to leave the
+            // ring; the last window of the task drains both queues.
             {
+                const bool last = wrel >= wlast;
                 const uint32_t next_w = (wrel >> 9) + 1;
-                while (q1n && q1_head + R <= next_w) round1();
+                uint32_t base = 0;
+                for (;;) {
+                    const uint32_t take = min(tot1 - base, kQueueCap - q1n);
+                    if (take) {
+                        if (q1n == 0) q1_head = wrel >> 9;
+                        uint32_t g = ex1 - base;  // rank of this lane's first survivor in this piece (wraps below 0 for those already pushed)
+                        uint32_t at = q1_s + (q1n + g) * 4u;
+                        const uint32_t pos0 = wrel + 16 * lane - 1;
+                        for (uint32_t m = m1; m; m &= m - 1, g++, at += 4)
+                            if (g < take) asm volatile("st.shared.u32 [%0], %1;\n" ::"r"(at), "r"(pos0 + (uint32_t)__ffs(m)) : "memory");
+                        q1n += take;
+                        base += take;
+                        __syncwarp();
+                    }
+                    const bool drain = last && base >= tot1;
+                    for (;;) {
+                        const bool do2 = q2n > 32 || (drain && q1n == 0 && q2n != 0);
+                        const bool do1 = q1n >= 32 || (q1n != 0 && (drain || q1_head + R <= next_w));
+                        if (do2)
+                            round2();
+                        else if (do1)
+                            round1();
+                        else
+                            break;
+                    }
+                    if (base >= tot1) break;
+                }
+                if (last) break;
             }
             __syncwarp();  // every lane is done with the slot before its history is replaced
-            if (lane == 31) sts128(text_s(wrel + kWin) - 16, cur);
+            cur_slot += kSlotBytes;
+            if (cur_slot == ring_end) cur_slot = ring_s;
+            if (lane == 31) sts128(cur_slot, cur);  // the next window's history
             carry_z = __shfl_sync(0xffffffffu, cur.z, 31);
             carry_w = __shfl_sync(0xffffffffu, cur.w, 31);
-            cur = nx1;
-            nx1 = nx2;
+            cur = nxt;
         }
-        while (q1n) round1();
-        while (q2n) round2();
         if (lane == 0) out.unit_counts[task] = n_emitted;
         if (CP && lane == 0) task_cont[task] = cp_before;
         __syncwarp();

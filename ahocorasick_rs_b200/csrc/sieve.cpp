@@ -170,6 +170,34 @@ uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_
         }
     }
     if (bloom_bytes_max < 1024) bloom_bytes_max = 1024;
+    // ---- filters against text ring ---------------------------------------------------------------
+    // bloom_bytes_max is what the filters may take when each warp of the scan keeps ONE window of text on chip.  A warp
+    // has to finish the survivors of a window before that window's slot in its ring is overwritten, so with a ring of one
+    // stage 1 runs after every window that has a survivor, however few lanes that fills; with a ring of r it waits
+    // for 32 of them (or r windows).  A deeper ring costs kSieveScanWarps x kSieveRingSlotBytes of filter per extra
+    // window, i.e. a denser primary bitmap and more chance survivors.  Stage-1 rounds per window are about
+    // max(chance survivors / 32, 1 / r): take a deeper ring while that drops by a quarter or more.  (Dense pattern sets
+    // keep the ring of one -- their rounds are full anyway; a few thousand patterns get 4 or 8 windows.)  The kernel
+    // launch sizes the ring from the shared memory the filters leave, so nothing else has to know.
+    {
+        auto rounds = [&](uint32_t r, uint64_t bytes) {
+            uint64_t pb = std::min<uint64_t>(uint64_t(n_keys) * 256, bytes * 8 * 7 / 10);
+            pb = std::max<uint64_t>(pb, 4096);
+            const double chance = 512.0 * double(n_keys) / double(pb);
+            return std::max(chance / 32.0, 1.0 / double(r));
+        };
+        double best = rounds(1, bloom_bytes_max);
+        uint32_t budget = bloom_bytes_max;
+        for (uint32_t r = 2; r <= 8; r *= 2) {
+            const uint64_t extra = uint64_t(kSieveScanWarps) * (r - 1) * kSieveRingSlotBytes;
+            if (uint64_t(bloom_bytes_max) < extra + 16384) break;
+            const double c = rounds(r, bloom_bytes_max - extra);
+            if (c > 0.75 * best) break;
+            best = c;
+            budget = (uint32_t)(bloom_bytes_max - extra);
+        }
+        bloom_bytes_max = budget;
+    }
     const uint64_t max_bits = uint64_t(bloom_bytes_max) * 8;
     // The primary bitmap (one bit per W-byte suffix, the only thing the fast path looks at) is kept sparse -- its fill
     // is the share of text positions that need a second look -- but never takes more than 70 % of the budget.

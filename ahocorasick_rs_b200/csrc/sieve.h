@@ -47,6 +47,9 @@ constexpr uint32_t kSieveMagic = 0x32424341u;  // "ACB2"
 constexpr uint32_t kSieveMaxW = 8;             // the primary window: W = min(shortest pattern, 8) bytes at most
 constexpr uint32_t kSieveMaxLevel = 16;        // deepest suffix length the on-chip filter may hold (the kernel keeps 16 bytes of history on chip)
 constexpr uint32_t kSieveNoNode = 0xffffffffu;
+// geometry of the scan kernel's shared memory that the builder sizes the filters against (scan_sieve.cuh asserts both)
+constexpr uint32_t kSieveScanWarps = 24;       // warps per CTA
+constexpr uint32_t kSieveRingSlotBytes = 576;  // one window of text in a warp's ring
 
 // ---- hashing --------------------------------------------------------------------------------
 // A window of d bytes ending at position e is identified by a 32-bit value x_d:
@@ -126,7 +129,8 @@ struct SieveNodeB {           // what the emission reads
 constexpr uint32_t kNodeTerminal = 1u << 17;
 
 struct Automaton;
-// Builds the sieve image for the automaton's patterns.  bloom_bytes_max: the shared memory the filter may take.
+// Builds the sieve image for the automaton's patterns.  bloom_bytes_max: the shared memory the filters may take when the
+// scan keeps one window of text per warp on chip (the builder may use less, to leave room for a deeper ring: sieve.cpp).
 // w_max: cap on the primary window (0 = automatic).
 uint64_t sieve_image_build(const uint8_t *blob, const uint64_t *offsets, uint64_t n, uint32_t bloom_bytes_max, uint32_t w_max,
                            std::vector<uint8_t> &out);

@@ -133,8 +133,9 @@ int acb_hot_describe(const void *host_hot, acb_hot_desc *desc);
  * selected from it per haystack for all three match kinds.  This is the compact (non-DFA) table format: a few tens of
  * bytes per trie node instead of a dense row per state.
  * acb_sieve_build builds (or rebuilds, when the arguments change) the image on the host and returns its size (0 on
- * error): bloom_bytes_max = shared memory the filter may take (the caller knows the device), w_max = cap on the primary
- * window in bytes (0 = automatic).  The caller uploads acb_sieve_write()'s copy and passes the device pointer to the
+ * error): bloom_bytes_max = shared memory the filters may take when the scan keeps one 512-byte window of text per warp
+ * on chip (the caller knows the device: shared memory per block minus 46 KB; the builder uses less for sparse pattern sets,
+ * which leaves the scan a deeper ring of text), w_max = cap on the primary window in bytes (0 = automatic).  The caller uploads acb_sieve_write()'s copy and passes the device pointer to the
  * scans as dev_sieve (NULL = use the table kernels).
  */
 uint64_t acb_sieve_build(acb_automaton *a, uint32_t bloom_bytes_max, uint32_t w_max);
