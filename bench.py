@@ -183,7 +183,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def make_dense(pats, data, offs, seed=7):
@@ -223,6 +223,26 @@ def device_random_lowercase(torch, dev, n_bytes: int, seed: int):
     return out
 
 
+_RESULT_OUT = None   # the process's real stdout, once claim_stdout() has pointed fd 1 at stderr
+
+
+def claim_stdout():
+    """stdout carries ONE JSON line.  Libraries write to fd 1 behind Python's back (NCCL prints "NCCL version ..." there
+    at every debug level but NONE), so fd 1 is pointed at stderr for the whole run and the result line goes to a
+    duplicate of the original descriptor."""
+    global _RESULT_OUT
+    if _RESULT_OUT is None:
+        sys.stdout.flush()
+        _RESULT_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _RESULT_OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -242,6 +262,7 @@ def main():
     ap.add_argument("--table", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    claim_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -262,10 +283,6 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # stdout carries ONE JSON line: keep NCCL's "NCCL version ..." banner (printed to stdout at the VERSION debug
-        # level) out of it; anything more verbose that the caller asked for is left alone
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
 
     L = _capi.lib()
@@ -532,7 +549,7 @@ def main():
         line["cpu_baseline"] = {"value": gbs, "unit": "GB/s", "cores": threads, "kind": "port", "matches_per_s": mps,
                                 "sample": f"{(soffs[-1] - soffs[0]) / 1e6:.1f} MB of the same workload ({len(soffs) - 1} haystacks) x {reps} passes inside one thread launch, "
                                           f"{threads} threads, one contiguous shard per thread"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
