@@ -94,3 +94,24 @@ def test_high_bytes_and_binary_patterns():
     offs = np.array([0, 1000, 3000], dtype=np.int64)
     img = SieveImage(pats, 0)
     assert scan(img, data, offs, True) == oracle_rows(pats, "Standard", data, offs, True)
+
+
+def test_filters_leave_room_for_a_deeper_ring_on_sparse_sets():
+    """csrc/sieve.cpp: the builder gives up filter bytes for a deeper ring of text per warp (24 warps x 576 B per extra
+    window) while that cuts the estimated stage-1 rounds per window by a quarter or more; dense sets keep every byte."""
+    budget = 232448 - 46 * 1024
+    slot = 24 * 576
+    rng = np.random.default_rng(7)
+    al = np.frombuffer(b"abcdefghijklmnopqrstuvwxyz", dtype=np.uint8)
+
+    def pats(n, lo, hi):
+        return [bytes(al[rng.integers(0, 26, size=int(rng.integers(lo, hi + 1)))]) for _ in range(n)]
+
+    dense = SieveImage(pats(50_000, 5, 12), 0, budget)          # ~50 k keys: chance survivors fill a round per window
+    assert budget - slot < dense.bloom_words * 4 <= budget
+    mid = SieveImage(pats(10_000, 5, 12), 0, budget)            # ~10 k keys: a ring of four windows
+    assert budget - 4 * slot < mid.bloom_words * 4 <= budget - 3 * slot
+    few = SieveImage(pats(2_000, 5, 12), 0, budget)             # a ring of eight
+    assert few.bloom_words * 4 <= budget - 7 * slot
+    # the primary bitmap stays the sparse part: at most one bit in 64 set by chance on the sparse sets
+    assert few.n_keys * 64 <= few.prim_words * 32 and mid.n_keys * 64 <= mid.prim_words * 32
