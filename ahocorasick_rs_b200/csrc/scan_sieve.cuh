@@ -1,6 +1,6 @@
 // scan_sieve.cuh -- the position-parallel scan (see sieve.h for the idea and the image).
 //
-// One persistent CTA per SM, 32 warps.  Dynamic shared memory:
+// One persistent CTA per SM, 24 warps.  Dynamic shared memory:
 //   [ primary bitmap | secondary Bloom filter : bloom_words x u32 ]   one TMA bulk copy (cp.async.bulk + mbarrier)
 //   [ mbarrier ]
 //   [ per warp: R x (16 B history | 512 B window) | 16 B pad ]   the "stash": a ring of the last R windows of text the
@@ -12,7 +12,8 @@
 //
 // Work: the byte stream is cut into TASKS of task_bytes (a multiple of 512) on a grid anchored at a 512-byte aligned
 // address; warps claim tasks from an atomic counter and walk them in 512-byte WINDOWS: lane l holds bytes
-// [16 l, 16 l + 16) of the window in registers (one coalesced LDG.128 per lane, two windows prefetched ahead).
+// [16 l, 16 l + 16) of the window in registers (one coalesced LDG.128 per lane; the next window's load is in flight
+// while this one is scanned).
 //
 // Per window:
 //   fast path   for each of its 16 bytes a lane forms the W-byte window ending there (funnel shifts over its own words and
@@ -28,6 +29,7 @@
 //               node = every pattern ending there; matches are written with ONE atomicAdd per round (warp-aggregated
 //               reservation; ranks by shuffle prefix sums), each tagged with (task, rank in task) so that the epilogue
 //               can place it without a sort.  Both queues are first-in first-out, so matches leave in stream order.
+//   The queueing and the two stages exist once in the code: a service loop after every window decides which runs.
 //
 // Output of this kernel = the OVERLAPPING match list.  sieve_epilogue_kernel (capi.cu) orders it and, for the
 // non-overlapping searches, selects from it per haystack.
